@@ -1,0 +1,192 @@
+/* mahi-mpc-b200 -- C ABI of the B200-native multiple-shooting MPC hot path.
+ *
+ * This is the drop-in boundary: plain C, opaque handles, caller-owned buffers, no exceptions and no
+ * C++/torch types.  Everything the reference does between "ModelControl::calc_u hands vectors to
+ * casadi::nlpsol" and "gets res["x"] back" (src/Mahi/Mpc/ModelControl.cpp:116-172) happens behind
+ * mmpc_solve(); the CasADi-generated nlp_* callbacks (emitted by ModelGenerator.cpp:238) are behind
+ * mmpc_nlp_eval() / mmpc_eval_nodes().  The C++ facade in include/Mahi/Mpc/ *.hpp (same class and
+ * method names as the reference) is a thin layer over these calls; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns MMPC_OK (0) or a negative mmpc_status; mmpc_last_error() gives the
+ *     thread-local message of the last failure on the calling thread;
+ *   - all arithmetic is fp64; vectors are dense `double`, laid out exactly as the reference lays
+ *     them out (V, p, g: ModelGenerator.cpp:61-112,129-187,206-225), instance-major for batches;
+ *   - a pointer argument is a HOST pointer if `mem == MMPC_MEM_HOST`, a DEVICE pointer (on the
+ *     solver's device) if `mem == MMPC_MEM_DEVICE`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the handle's own stream); calls are
+ *     synchronous w.r.t. the host for MMPC_MEM_HOST and stream-ordered for MMPC_MEM_DEVICE;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     MMPC_ERR_NO_DEVICE.
+ */
+#ifndef MAHI_MPC_B200_H
+#define MAHI_MPC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMPC_ABI_VERSION 1
+
+typedef enum mmpc_status {
+    MMPC_OK = 0,
+    MMPC_ERR_INVALID = -1,    /* bad argument / size mismatch */
+    MMPC_ERR_NO_DEVICE = -2,  /* no usable CUDA device (there is no CPU path) */
+    MMPC_ERR_CUDA = -3,       /* CUDA runtime error, see mmpc_last_error() */
+    MMPC_ERR_IO = -4,         /* model artefact missing / unreadable */
+    MMPC_ERR_UNKNOWN_MODEL = -5,
+    MMPC_ERR_ALLOC = -6,
+    MMPC_ERR_UNSUPPORTED = -7
+} mmpc_status;
+
+typedef enum mmpc_mem { MMPC_MEM_HOST = 0, MMPC_MEM_DEVICE = 1 } mmpc_mem;
+
+/* integrator of the one-step map F: EULER is what the library's NLP uses
+ * (ModelGenerator.cpp:33-34); RK4 (x `substeps`) is the MATLAB prototypes' (workingMPC_8_30_21.m:46-59). */
+typedef enum mmpc_integrator { MMPC_EULER = 0, MMPC_RK4 = 1 } mmpc_integrator;
+
+/* per-instance solve status (the reference never inspects IPOPT's, ModelControl.cpp:159-160) */
+typedef enum mmpc_solve_status {
+    MMPC_SOLVE_CONVERGED = 0,
+    MMPC_SOLVE_MAX_ITER = 1,
+    MMPC_SOLVE_NUMERICAL = 2 /* NaN/Inf or regularisation exhausted */
+} mmpc_solve_status;
+
+typedef struct mmpc_model* mmpc_model_t;
+typedef struct mmpc_solver* mmpc_solver_t;
+
+/* Field-for-field mirror of mahi::mpc::ModelParameters (include/Mahi/Mpc/ModelParameters.hpp:11-28);
+ * times in microseconds as in the JSON artefact (ModelParameters.cpp:37-50). Bound pointers may be
+ * NULL (= the reference's "no bound" sentinel +-10e30, ModelParameters.cpp:21-24). */
+typedef struct mmpc_model_params {
+    const char* name;
+    long long timespan_us;
+    long long step_size_us;
+    int num_x;
+    int num_u;
+    int num_shooting_nodes;
+    const double* x_min;
+    const double* u_min;
+    const double* x_max;
+    const double* u_max;
+    const char* dll_filepath; /* "<name>.so" (generated CUDA model library) or "builtin:<kernel set>" */
+    int is_linear;
+} mmpc_model_params;
+
+/* Solver options. Defaults = the reference's hard-coded IPOPT options (ModelControl.cpp:54-59). */
+typedef struct mmpc_options {
+    double tol;            /* 1e-5  scaled KKT error (IPOPT "tol") */
+    int max_iter;          /* 200 */
+    int integrator;        /* MMPC_EULER */
+    int substeps;          /* 1 */
+    double mu_init;        /* 0.1   barrier start when finite bounds exist (IPOPT mu_init) */
+    int warm_start;        /* 1: start from the previous solution of the same instance slot
+                                 (ModelControl.cpp:161: args["x0"] = result), 0: always cold (zeros) */
+    int warm_start_duals;  /* 0: reference behaviour (primal only); 1: also reuse lam_g */
+    int kernel_variant;    /* 0 = auto; see DESIGN.md "kernels" */
+    int reserved[8];
+} mmpc_options;
+
+/* Per-instance statistics returned by mmpc_solve (40 bytes). */
+typedef struct mmpc_stats {
+    double objective;  /* f at the returned point */
+    double kkt_error;  /* scaled optimality error at the returned point */
+    double mu;         /* final barrier parameter (0 if no finite bounds) */
+    int iterations;
+    int status;        /* mmpc_solve_status */
+    int ls_steps;      /* total backtracking steps */
+    int reg_steps;     /* total Hessian regularisation retries */
+} mmpc_stats;
+
+const char* mmpc_last_error(void);
+int mmpc_abi_version(void);
+int mmpc_device_count(int* count);
+int mmpc_options_default(mmpc_options* opts);
+
+/* ---- model artefact -------------------------------------------------------------------------
+ * replaces ModelControl::load_model's json + nlpsol(dll) + casadi::external loading
+ * (src/Mahi/Mpc/ModelControl.cpp:21-26,61-62,70-72). */
+int mmpc_model_create(const mmpc_model_params* params, mmpc_model_t* out);
+/* reads "<model_name>.json" in the reference's schema (ModelParameters.cpp:37-72) */
+int mmpc_model_load(const char* model_name, mmpc_model_t* out);
+int mmpc_model_free(mmpc_model_t model);
+/* nx, nu, N, NV = nx(N+1)+nu N, M = N nx, np = length of p (ModelGenerator.cpp:61,129-143) */
+int mmpc_model_dims(mmpc_model_t model, int* nx, int* nu, int* N, int* NV, int* M, int* np);
+int mmpc_model_step_size(mmpc_model_t model, double* seconds);
+int mmpc_model_is_linear(mmpc_model_t model, int* is_linear);
+/* straight-line op counts of the generated device code (arith, transcendental) for f, f+A+B, f+A+B+H */
+int mmpc_model_op_counts(mmpc_model_t model, int counts[6]);
+
+/* ---- <name>_get_A / _get_B / _get_x_dot_init (ModelGenerator.cpp:51-53; ModelControl.cpp:127-133)
+ * n points; x[n*nx], u[n*nu] -> xdot[n*nx], A[n*nx*nx], B[n*nx*nu], A and B COLUMN-major per point
+ * (the order ModelControl flattens them into p). Any output may be NULL. */
+int mmpc_linearise(mmpc_model_t model, int device, int n, const double* x, const double* u, double* xdot, double* A,
+                   double* B, mmpc_mem mem, void* stream);
+
+/* ---- shooting-node evaluation (BASELINE config 5; SURVEY 8 a-2,a-5,a-7,a-8) --------------------
+ * n independent nodes, STRUCTURE-OF-ARRAYS: component i of node j at [i*n + j].
+ *   in : x[nx*n], u[nu*n], x_next[nx*n], w[nx*n] (may be NULL)
+ *   out: g[nx*n]      = F(x,u) - x_next
+ *        Fx[nx*nx*n]  = dF/dx  (entry (r,c) at [(r*nx+c)*n + j])
+ *        Fu[nx*nu*n]  = dF/du
+ *        H[s(s+1)/2*n] = sum_i w_i d2F_i/dz2, packed upper triangle row-major, only if w != NULL
+ * All pointers in `mem` space. */
+int mmpc_eval_nodes(mmpc_model_t model, int device, const mmpc_options* opts, long long n, const double* x, const double* u,
+                    const double* x_next, const double* w, double* g, double* Fx, double* Fu, double* H, mmpc_mem mem,
+                    void* stream);
+
+/* ---- whole-NLP callbacks, batched: nlp_f, nlp_g, nlp_grad_f, nlp_jac_g, nlp_hess_l -------------
+ * (the functions CasADi generates from ModelGenerator.cpp:225-232,238).  Instance-major AoS inputs in the
+ * reference's layouts: V[B*NV], p[B*np], lam_g[B*M]; outputs (any may be NULL):
+ *   f[B], g[B*M], grad_f[B*NV],
+ *   jac blocks  Fx[B*N*nx*nx], Fu[B*N*nx*nu] (row-major per node; d g_k/d x_{k+1} = -I is implicit),
+ *   hess blocks Hzz[B*N*s*s] (row-major full stage blocks of lam_f*f + lam_g'g w.r.t. z_k=(x_k,u_k);
+ *   the (u_k,u_{k+1}) coupling block is -2*lam_f*diag(R), the x_N block is zero). */
+int mmpc_nlp_eval(mmpc_model_t model, int device, const mmpc_options* opts, int batch, const double* V, const double* p,
+                  const double* lam_g, double lam_f, double* f, double* g, double* grad_f, double* Fx, double* Fu,
+                  double* Hzz, mmpc_mem mem, void* stream);
+
+/* ---- solver ---------------------------------------------------------------------------------- */
+int mmpc_solver_create(mmpc_model_t model, int device, int batch, const mmpc_options* opts, mmpc_solver_t* out);
+int mmpc_solver_free(mmpc_solver_t solver);
+int mmpc_solver_batch(mmpc_solver_t solver, int* batch);
+int mmpc_set_options(mmpc_solver_t solver, const mmpc_options* opts);
+/* Q[nx], R[nu], Rm[nu] shared by all instances (per_instance = 0) or Q[B*nx] ... (per_instance = 1);
+ * HOST pointers. Mirrors ModelControl ctor / update_weights (ModelControl.cpp:7-14,199-203): a NULL
+ * pointer leaves that weight unchanged. */
+int mmpc_set_weights(mmpc_solver_t solver, const double* Q, const double* R, const double* Rm, int per_instance);
+/* x_min/x_max[nx], u_min/u_max[nu], HOST pointers, NULL = keep. |b| >= 1e19 means "no bound"
+ * (ModelControl::update_control_limits, ModelControl.cpp:205-209; IPOPT nlp_*_bound_inf). */
+int mmpc_set_bounds(mmpc_solver_t solver, const double* x_min, const double* x_max, const double* u_min, const double* u_max);
+/* forget the stored warm start (next solve starts from zeros, ModelControl.cpp:28-50,68) */
+int mmpc_reset_warm_start(mmpc_solver_t solver);
+
+/* One batched solve = `batch` independent ModelControl::calc_u calls (ModelControl.cpp:116-163).
+ *   state[B*nx]   current state, pinned as x_0           (ModelControl.cpp:144-145)
+ *   control[B*nu] previous control = u_init in p         (ModelControl.cpp:136)
+ *   traj[B*N*nx]  reference r_0..r_{N-1}                 (ModelControl.cpp:116,120)
+ *   V_out[B*NV]   res["x"] in the reference layout       (ModelControl.cpp:160)
+ *   lam_out[B*M]  constraint multipliers (may be NULL)
+ *   stats[B]      (may be NULL)
+ * For is_linear models A, B, xdot_init are computed on the device at (state, control)
+ * (ModelControl.cpp:125-135). */
+int mmpc_solve(mmpc_solver_t solver, const double* state, const double* control, const double* traj, double* V_out,
+               double* lam_out, mmpc_stats* stats, mmpc_mem mem, void* stream);
+
+/* Time of the device work of the last mmpc_solve on this handle in milliseconds (CUDA events on the
+ * launching stream): [0] H2D staging, [1] kernels, [2] D2H staging. */
+int mmpc_last_timing(mmpc_solver_t solver, double ms[3]);
+/* number of kernels the last mmpc_solve launched */
+int mmpc_last_launch_count(mmpc_solver_t solver, int* launches);
+
+/* ---- measurement utility ----------------------------------------------------------------------
+ * Measured fp64 FMA throughput of `device` in TFLOP/s (independent DFMA chains, every SM busy,
+ * CUDA-event timed) -- the denominator of the solve kernels' FP64 roofline fraction
+ * (MEASURED_PEAKS.json has no fp64 entry). */
+int mmpc_measure_fp64_peak(int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAHI_MPC_B200_H */

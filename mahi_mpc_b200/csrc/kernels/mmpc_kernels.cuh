@@ -1,0 +1,799 @@
+// mahi-mpc-b200 :: sm_100a kernels of the multiple-shooting MPC hot path, templated on a generated
+// model functor `M` (struct mmpc_model_<name>: NX, NU, f, fAB, fABH -- see csrc/modelgen/codegen.cpp).
+//
+// What replaces what (reference file:line):
+//   eval_nodes_kernel   the per-node body of the CasADi-generated nlp_g / nlp_jac_g / nlp_hess_l
+//                       (node loop ModelGenerator.cpp:191-222; F = x + h f, :33-34)           SURVEY 8 a-2,a-5,a-7,a-8
+//   linearise_kernel    <name>_get_A/_get_B/_get_x_dot_init (ModelGenerator.cpp:45-46,51-53)      SURVEY 8 a-9
+//   nlp_eval_kernel     nlp_f, nlp_g, nlp_grad_f, nlp_jac_g, nlp_hess_l in the reference layouts    SURVEY 8 a-5..a-8
+//   solve_kernel        m_solver(m_solver_args) = IPOPT + MUMPS (ModelControl.cpp:159): here an exact-Hessian
+//                       Newton / primal-dual interior-point iteration whose KKT system is solved by a
+//                       stage-wise Riccati recursion on the augmented state (x_k, u_{k-1})           SURVEY 8 a-10
+//
+// All arithmetic fp64 on the DFMA pipe; no tensor cores (tcgen05 has no fp64 type).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../../include/mahi_mpc_b200.h"
+#include "mmpc_vtable.h"
+
+namespace mmpc {
+
+#define MMPC_UNROLL _Pragma("unroll")
+
+template <class M>
+struct Dim {
+    static constexpr int NX = M::NX, NU = M::NU, S = NX + NU, NH = S * (S + 1) / 2;
+};
+
+// packed upper-triangular index (row-major), requires i <= j
+__host__ __device__ constexpr int tri(int i, int j, int S) { return i * S - (i * (i - 1)) / 2 + (j - i); }
+__host__ __device__ constexpr int trisym(int i, int j, int S) { return i <= j ? tri(i, j, S) : tri(j, i, S); }
+
+// ---------------------------------------------------------------------------------------------
+// one-step map F and its derivatives (explicit Euler: F = x + h f, ModelGenerator.cpp:33-34)
+//   WANT 0: F          1: F, Fx, Fu        2: F, Fx, Fu, Hs
+// Hs = sum_i w_i d2F_i/dz2 (packed upper triangle) with the NLP's weights
+//   w_i = wq_i * e_i + lam_i,  e_i = F_i - r_i   (wq = 2*lam_f*Q for nlp_hess_l; 0 for a plain contraction)
+// Because e depends on f itself, the generated functor takes the weights in affine form
+//   w_i = wa_i f_i + wb_i,  wa_i = wq_i h^2,  wb_i = h (wq_i (x_i - r_i) + lam_i).
+// ---------------------------------------------------------------------------------------------
+template <class M, int WANT>
+__device__ __forceinline__ void step_euler(double h, const double* x, const double* u, const double* wq, const double* r,
+                                           const double* lam, double* F, double* Fx, double* Fu, double* Hs) {
+    constexpr int NX = M::NX, NU = M::NU;
+    double xd[NX];
+    if (WANT == 0) {
+        M::f(x, u, xd);
+    } else if (WANT == 1) {
+        M::fAB(x, u, xd, Fx, Fu);
+    } else {
+        double wa[NX], wb[NX];
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            wa[i] = wq[i] * h * h;
+            wb[i] = h * (wq[i] * (x[i] - r[i]) + lam[i]);
+        }
+        M::fABH(x, u, wa, wb, xd, Fx, Fu, Hs);
+    }
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) F[i] = fma(h, xd[i], x[i]);
+    if (WANT >= 1) {
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            MMPC_UNROLL for (int j = 0; j < NX; ++j) Fx[i * NX + j] = (i == j ? 1.0 : 0.0) + h * Fx[i * NX + j];
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) Fu[i * NU + j] = h * Fu[i * NU + j];
+        }
+    }
+}
+
+// linearised one-step map F_lin = x + h (A (x - x_init) + B (u - u_init) + xdot_init) (ModelGenerator.cpp:47-48)
+// A, B row-major here.
+template <class M, int WANT>
+__device__ __forceinline__ void step_linear(double h, const double* x, const double* u, const double* A, const double* B,
+                                            const double* xdot0, const double* x_init, const double* u_init, double* F,
+                                            double* Fx, double* Fu, double* Hs) {
+    constexpr int NX = M::NX, NU = M::NU;
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+        double acc = xdot0[i];
+        MMPC_UNROLL for (int j = 0; j < NX; ++j) acc = fma(A[i * NX + j], x[j] - x_init[j], acc);
+        MMPC_UNROLL for (int j = 0; j < NU; ++j) acc = fma(B[i * NU + j], u[j] - u_init[j], acc);
+        F[i] = fma(h, acc, x[i]);
+    }
+    if (WANT >= 1) {
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            MMPC_UNROLL for (int j = 0; j < NX; ++j) Fx[i * NX + j] = (i == j ? 1.0 : 0.0) + h * A[i * NX + j];
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) Fu[i * NU + j] = h * B[i * NU + j];
+        }
+    }
+    if (WANT >= 2) {
+        MMPC_UNROLL for (int i = 0; i < Dim<M>::NH; ++i) Hs[i] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// eval_nodes: n independent shooting nodes, SoA in / SoA out, one thread per node (HBM-bound stream)
+// ---------------------------------------------------------------------------------------------
+template <class M, bool WITH_H>
+__global__ void __launch_bounds__(128) eval_nodes_kernel(double h, long long n, const double* __restrict__ x,
+                                                         const double* __restrict__ u, const double* __restrict__ xn,
+                                                         const double* __restrict__ w, double* __restrict__ g,
+                                                         double* __restrict__ Fx, double* __restrict__ Fu,
+                                                         double* __restrict__ H) {
+    constexpr int NX = M::NX, NU = M::NU, NH = Dim<M>::NH;
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+        double xr[NX], ur[NU], F[NX], fx[NX * NX], fu[NX * NU];
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) xr[i] = x[i * n + j];
+        MMPC_UNROLL for (int i = 0; i < NU; ++i) ur[i] = u[i * n + j];
+        if (WITH_H) {
+            double wr[NX], zero[NX], hs[NH];
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+                wr[i] = w[i * n + j];
+                zero[i] = 0.0;
+            }
+            step_euler<M, 2>(h, xr, ur, zero, zero, wr, F, fx, fu, hs);
+            MMPC_UNROLL for (int i = 0; i < NH; ++i) __stcs(&H[i * n + j], hs[i]);
+        } else {
+            step_euler<M, 1>(h, xr, ur, nullptr, nullptr, nullptr, F, fx, fu, nullptr);
+        }
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) __stcs(&g[i * n + j], F[i] - xn[i * n + j]);
+        MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) __stcs(&Fx[i * n + j], fx[i]);
+        MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) __stcs(&Fu[i * n + j], fu[i]);
+    }
+}
+
+// <name>_get_x_dot_init/_get_A/_get_B: AoS, A and B column-major per point (ModelControl.cpp:127-133)
+template <class M>
+__global__ void linearise_kernel(int n, const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ xdot,
+                                 double* __restrict__ A, double* __restrict__ B) {
+    constexpr int NX = M::NX, NU = M::NU;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double xr[NX], ur[NU], xd[NX], a[NX * NX], b[NX * NU];
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) xr[i] = x[(size_t)j * NX + i];
+    MMPC_UNROLL for (int i = 0; i < NU; ++i) ur[i] = u[(size_t)j * NU + i];
+    M::fAB(xr, ur, xd, a, b);
+    if (xdot) MMPC_UNROLL for (int i = 0; i < NX; ++i) xdot[(size_t)j * NX + i] = xd[i];
+    if (A) MMPC_UNROLL for (int r = 0; r < NX; ++r) MMPC_UNROLL for (int c = 0; c < NX; ++c) A[(size_t)j * NX * NX + c * NX + r] = a[r * NX + c];
+    if (B) MMPC_UNROLL for (int r = 0; r < NX; ++r) MMPC_UNROLL for (int c = 0; c < NU; ++c) B[(size_t)j * NX * NU + c * NX + r] = b[r * NU + c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// views of the reference's parameter vector p (ModelGenerator.cpp:129-187)
+// ---------------------------------------------------------------------------------------------
+template <class M>
+struct PView {
+    const double *r, *Q, *R, *Rm, *A, *B, *xdot_init, *x_init, *u_init;
+    __host__ __device__ static int np(int N, int is_linear) {
+        return N * M::NX + M::NX + 3 * M::NU + (is_linear ? M::NX * M::NX + M::NX * M::NU + 2 * M::NX : 0);
+    }
+    __device__ PView(const double* p, int N, int is_linear) {
+        r = p; p += N * M::NX;
+        Q = p; p += M::NX;
+        R = p; p += M::NU;
+        Rm = p; p += M::NU;
+        A = B = xdot_init = x_init = nullptr;
+        if (is_linear) {
+            A = p; p += M::NX * M::NX;
+            B = p; p += M::NX * M::NU;
+            xdot_init = p; p += M::NX;
+            x_init = p; p += M::NX;
+        }
+        u_init = p;
+    }
+};
+
+// One (instance, node) of the whole-NLP callbacks. grid: (ceil(N/128), B), block 128.
+// f and grad_f are accumulated with atomics (f[b] and the u_{k-1} coupling entries), so the caller
+// zero-fills them first.
+template <class M>
+__global__ void __launch_bounds__(128) nlp_eval_kernel(mmpc_problem P, int B, const double* __restrict__ V,
+                                                       const double* __restrict__ p, const double* __restrict__ lamg,
+                                                       double lam_f, double* __restrict__ f, double* __restrict__ g,
+                                                       double* __restrict__ grad_f, double* __restrict__ Fx,
+                                                       double* __restrict__ Fu, double* __restrict__ Hzz) {
+    constexpr int NX = M::NX, NU = M::NU, S = Dim<M>::S, NH = Dim<M>::NH;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y, N = P.N;
+    if (k >= N || b >= B) return;
+    const int NV = NX * (N + 1) + NU * N, Mc = N * NX;
+    const double* Vb = V + (size_t)b * NV;
+    const PView<M> pv(p + (size_t)b * PView<M>::np(N, P.is_linear), N, P.is_linear);
+    double x[NX], u[NU], up[NU], xn[NX], r[NX], lam[NX], wq[NX], F[NX], fx[NX * NX], fu[NX * NU], hs[NH], e[NX];
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+        x[i] = Vb[k * S + i];
+        xn[i] = Vb[(k + 1) * S + i];
+        r[i] = pv.r[k * NX + i];
+        lam[i] = lamg ? lamg[(size_t)b * Mc + k * NX + i] : 0.0;
+        wq[i] = 2.0 * lam_f * pv.Q[i];
+    }
+    MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+        u[j] = Vb[k * S + NX + j];
+        up[j] = k ? Vb[(k - 1) * S + NX + j] : pv.u_init[j];
+    }
+    if (P.is_linear) {
+        double A[NX * NX], Bm[NX * NU];  // p holds them column-major
+        MMPC_UNROLL for (int rr = 0; rr < NX; ++rr) {
+            MMPC_UNROLL for (int c = 0; c < NX; ++c) A[rr * NX + c] = pv.A[c * NX + rr];
+            MMPC_UNROLL for (int c = 0; c < NU; ++c) Bm[rr * NU + c] = pv.B[c * NX + rr];
+        }
+        step_linear<M, 2>(P.h, x, u, A, Bm, pv.xdot_init, pv.x_init, pv.u_init, F, fx, fu, hs);
+    } else {
+        step_euler<M, 2>(P.h, x, u, wq, r, lam, F, fx, fu, hs);
+    }
+    double fk = 0.0;
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+        e[i] = F[i] - r[i];
+        fk = fma(pv.Q[i] * e[i], e[i], fk);
+        if (g) g[(size_t)b * Mc + k * NX + i] = F[i] - xn[i];
+    }
+    MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+        const double du = u[j] - up[j];
+        fk = fma(pv.R[j] * du, du, fk);
+        fk = fma(pv.Rm[j] * u[j], u[j], fk);
+    }
+    if (f) atomicAdd(&f[b], fk);
+    if (Fx) MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) Fx[((size_t)b * N + k) * NX * NX + i] = fx[i];
+    if (Fu) MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) Fu[((size_t)b * N + k) * NX * NU + i] = fu[i];
+    if (grad_f) {
+        double* gb = grad_f + (size_t)b * NV;
+        MMPC_UNROLL for (int j = 0; j < NX; ++j) {
+            double a = 0.0;
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) a = fma(fx[i * NX + j], 2.0 * pv.Q[i] * e[i], a);
+            gb[k * S + j] = a;  // x_k gets a contribution from node k only
+        }
+        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+            double a = 0.0;
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) a = fma(fu[i * NU + j], 2.0 * pv.Q[i] * e[i], a);
+            const double du = u[j] - up[j];
+            atomicAdd(&gb[k * S + NX + j], a + 2.0 * pv.R[j] * du + 2.0 * pv.Rm[j] * u[j]);
+            if (k) atomicAdd(&gb[(k - 1) * S + NX + j], -2.0 * pv.R[j] * du);
+        }
+        if (k == N - 1) MMPC_UNROLL for (int j = 0; j < NX; ++j) gb[N * S + j] = 0.0;
+    }
+    if (Hzz) {
+        double* Hb = Hzz + ((size_t)b * N + k) * S * S;
+        MMPC_UNROLL for (int a = 0; a < S; ++a) MMPC_UNROLL for (int c = 0; c < S; ++c) {
+            double acc = hs[trisym(a, c, S)];
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+                const double fa = a < NX ? fx[i * NX + a] : fu[i * NU + a - NX];
+                const double fc = c < NX ? fx[i * NX + c] : fu[i * NU + c - NX];
+                acc = fma(wq[i] * fa, fc, acc);
+            }
+            if (a == c && a >= NX) acc += 2.0 * lam_f * (pv.R[a - NX] + pv.Rm[a - NX]) + (k < N - 1 ? 2.0 * lam_f * pv.R[a - NX] : 0.0);
+            Hb[a * S + c] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// solve_kernel, variant T1: one thread per MPC instance, everything fused.
+//
+// Per Newton iteration (unbounded case; the problem is equality-constrained because x_0 is pinned,
+// ModelControl.cpp:144-145, and all other bounds default to +-10e30):
+//   backward sweep k = N-1..0 : evaluate F, Fx, Fu, Lagrangian stage Hessian at (z_k, lam_k); accumulate the
+//                               KKT residual norms of the CURRENT iterate; Riccati update of the value
+//                               function of the augmented state (x_k, u_{k-1}); store gains and P.
+//   -> converged? (IPOPT's scaled optimality error <= tol)  -> write out
+//   forward sweep k = 0..N-1  : dz from the gains, new multipliers from P, directional derivative of the l1 merit
+//                               function, and -- fused -- the merit value of the full step (alpha = 1)
+//   backtracking (rare)       : re-evaluate the merit at alpha/2, ...
+// ---------------------------------------------------------------------------------------------
+template <class M>
+struct RiccatiState {
+    double Pxx[M::NX * M::NX], Pxv[M::NX * M::NU], Pvv[M::NU * M::NU], px[M::NX], pv[M::NU];
+};
+
+// in-place Cholesky of the NU x NU matrix G (full storage, lower triangle used). returns false if not PD.
+template <int NU>
+__device__ __forceinline__ bool chol(double* G) {
+    bool ok = true;
+    MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+        double d = G[j * NU + j];
+        MMPC_UNROLL for (int k = 0; k < NU; ++k) if (k < j) d = fma(-G[j * NU + k], G[j * NU + k], d);
+        ok = ok && (d > 0.0) && isfinite(d);
+        const double l = sqrt(d > 0.0 ? d : 1.0), il = 1.0 / l;
+        G[j * NU + j] = l;
+        MMPC_UNROLL for (int i = 0; i < NU; ++i) if (i > j) {
+            double s = G[i * NU + j];
+            MMPC_UNROLL for (int k = 0; k < NU; ++k) if (k < j) s = fma(-G[i * NU + k], G[j * NU + k], s);
+            G[i * NU + j] = s * il;
+        }
+    }
+    return ok;
+}
+// solve L L' y = b in place (L from chol)
+template <int NU>
+__device__ __forceinline__ void chol_solve(const double* L, double* b) {
+    MMPC_UNROLL for (int i = 0; i < NU; ++i) {
+        double s = b[i];
+        MMPC_UNROLL for (int k = 0; k < NU; ++k) if (k < i) s = fma(-L[i * NU + k], b[k], s);
+        b[i] = s / L[i * NU + i];
+    }
+    MMPC_UNROLL for (int i = NU - 1; i >= 0; --i) {
+        double s = b[i];
+        MMPC_UNROLL for (int k = 0; k < NU; ++k) if (k > i) s = fma(-L[k * NU + i], b[k], s);
+        b[i] = s / L[i * NU + i];
+    }
+}
+
+template <class M>
+struct SolveCtx {
+    static constexpr int NX = M::NX, NU = M::NU, S = NX + NU, NH = S * (S + 1) / 2;
+    const mmpc_problem& P;
+    const mmpc_workspace& W;
+    const mmpc_solve_io& io;
+    int b;        // instance
+    size_t Bp;
+    double Q[NX], R[NU], Rm[NU], uinit[NU];
+    // linear-mode data (row-major A,B)
+    __device__ SolveCtx(const mmpc_problem& P_, const mmpc_workspace& W_, const mmpc_solve_io& io_, int b_)
+        : P(P_), W(W_), io(io_), b(b_), Bp(W_.Bp) {}
+    __device__ __forceinline__ double ld(const double* a, int row) const { return a[(size_t)row * Bp + b]; }
+    __device__ __forceinline__ void st(double* a, int row, double v) const { a[(size_t)row * Bp + b] = v; }
+    __device__ __forceinline__ double traj(int k, int i) const { return io.traj[((size_t)b * P.N + k) * NX + i]; }
+
+    // evaluate one node at (x,u) with the model or its linearisation
+    template <int WANT>
+    __device__ __forceinline__ void step(const double* x, const double* u, const double* wq, const double* r, const double* lam,
+                                         double* F, double* Fx, double* Fu, double* Hs) const {
+        if (P.is_linear) {
+            double A[NX * NX], Bm[NX * NU], xd0[NX], x0[NX];
+            MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) A[i] = ld(W.LIN, i);
+            MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) Bm[i] = ld(W.LIN, NX * NX + i);
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+                xd0[i] = ld(W.LIN, NX * NX + NX * NU + i);
+                x0[i] = ld(W.X, i);  // x_init = pinned state (ModelControl.cpp:134)
+            }
+            step_linear<M, WANT>(P.h, x, u, A, Bm, xd0, x0, uinit, F, Fx, Fu, Hs);
+        } else {
+            step_euler<M, WANT>(P.h, x, u, wq, r, lam, F, Fx, Fu, Hs);
+        }
+    }
+};
+
+struct SweepNorms {
+    double dual_inf, prim_inf, theta, fval, lam_l1;
+};
+
+// backward sweep; returns false if some G_uu was not positive definite (caller regularises and retries)
+template <class M>
+__device__ bool backward_sweep(const SolveCtx<M>& c, double delta, SweepNorms& nrm) {
+    constexpr int NX = M::NX, NU = M::NU, S = NX + NU, NH = S * (S + 1) / 2;
+    const int N = c.P.N;
+    RiccatiState<M> V;
+    MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) V.Pxx[i] = 0.0;
+    MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) V.Pxv[i] = 0.0;
+    MMPC_UNROLL for (int i = 0; i < NU * NU; ++i) V.Pvv[i] = 0.0;
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) V.px[i] = 0.0;
+    MMPC_UNROLL for (int i = 0; i < NU; ++i) V.pv[i] = 0.0;
+    double wq[NX];
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) wq[i] = 2.0 * c.Q[i];
+    double du_next[NU];  // R-weighted control increment of stage k+1 (enters the u_k stationarity residual)
+    MMPC_UNROLL for (int j = 0; j < NU; ++j) du_next[j] = 0.0;
+    double xn[NX], lam_next_unused = 0.0;
+    (void)lam_next_unused;
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) xn[i] = c.ld(c.W.X, N * NX + i);
+    nrm.dual_inf = nrm.prim_inf = nrm.theta = nrm.fval = nrm.lam_l1 = 0.0;
+    // stationarity w.r.t. x_N: -lam_{N-1} (x_N has no cost)
+    bool ok = true;
+    for (int k = N - 1; k >= 0; --k) {
+        double x[NX], u[NU], v[NU], r[NX], lam[NX], lam_prev[NX];
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            x[i] = c.ld(c.W.X, k * NX + i);
+            r[i] = c.traj(k, i);
+            lam[i] = c.ld(c.W.LAM, k * NX + i);
+            lam_prev[i] = k ? c.ld(c.W.LAM, (k - 1) * NX + i) : 0.0;
+        }
+        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+            u[j] = c.ld(c.W.U, k * NU + j);
+            v[j] = k ? c.ld(c.W.U, (k - 1) * NU + j) : c.uinit[j];
+        }
+        double F[NX], Fx[NX * NX], Fu[NX * NU], H[NH];
+        c.template step<2>(x, u, wq, r, lam, F, Fx, Fu, H);
+        double cres[NX], qe[NX];
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            const double e = F[i] - r[i];
+            cres[i] = F[i] - xn[i];
+            qe[i] = wq[i] * e;
+            nrm.fval = fma(c.Q[i] * e, e, nrm.fval);
+            nrm.prim_inf = fmax(nrm.prim_inf, fabs(cres[i]));
+            nrm.theta += fabs(cres[i]);
+            nrm.lam_l1 += fabs(lam[i]);
+        }
+        // objective gradient pieces
+        double qx[NX], qu[NU], qv[NU], dRu[NU];
+        MMPC_UNROLL for (int j = 0; j < NX; ++j) {
+            double a = 0.0, l = 0.0;
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+                a = fma(Fx[i * NX + j], qe[i], a);
+                l = fma(Fx[i * NX + j], lam[i], l);
+            }
+            qx[j] = a;
+            if (k) nrm.dual_inf = fmax(nrm.dual_inf, fabs(a + l - lam_prev[j]));
+        }
+        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+            double a = 0.0, l = 0.0;
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+                a = fma(Fu[i * NU + j], qe[i], a);
+                l = fma(Fu[i * NU + j], lam[i], l);
+            }
+            const double du = u[j] - v[j];
+            dRu[j] = 2.0 * c.R[j] * du;
+            qu[j] = a + dRu[j] + 2.0 * c.Rm[j] * u[j];
+            qv[j] = -dRu[j];
+            nrm.fval = fma(c.R[j] * du, du, nrm.fval);
+            nrm.fval = fma(c.Rm[j] * u[j], u[j], nrm.fval);
+            nrm.dual_inf = fmax(nrm.dual_inf, fabs(qu[j] + l - du_next[j]));
+            du_next[j] = dRu[j];
+        }
+        // full stage Hessian: H += Fz' (2Q) Fz ; uu diagonal += 2(R + Rm) (+ delta regularisation)
+        MMPC_UNROLL for (int a = 0; a < S; ++a) MMPC_UNROLL for (int d = a; d < S; ++d) {
+            double acc = H[tri(a, d, S)];
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+                const double fa = a < NX ? Fx[i * NX + a] : Fu[i * NU + a - NX];
+                const double fd = d < NX ? Fx[i * NX + d] : Fu[i * NU + d - NX];
+                acc = fma(wq[i] * fa, fd, acc);
+            }
+            if (a == d) acc += delta + (a >= NX ? 2.0 * (c.R[a - NX] + c.Rm[a - NX]) : 0.0);
+            H[tri(a, d, S)] = acc;
+        }
+        // ---- Riccati update ----
+        double y[NX], yv[NU];
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            double a = V.px[i];
+            MMPC_UNROLL for (int j = 0; j < NX; ++j) a = fma(V.Pxx[i * NX + j], cres[j], a);
+            y[i] = a;
+        }
+        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+            double a = V.pv[j];
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) a = fma(V.Pxv[i * NU + j], cres[i], a);
+            yv[j] = a;
+        }
+        double PA[NX * NX], PB[NX * NU];
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            MMPC_UNROLL for (int j = 0; j < NX; ++j) {
+                double a = 0.0;
+                MMPC_UNROLL for (int l = 0; l < NX; ++l) a = fma(V.Pxx[i * NX + l], Fx[l * NX + j], a);
+                PA[i * NX + j] = a;
+            }
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+                double a = V.Pxv[i * NU + j];
+                MMPC_UNROLL for (int l = 0; l < NX; ++l) a = fma(V.Pxx[i * NX + l], Fu[l * NU + j], a);
+                PB[i * NU + j] = a;
+            }
+        }
+        double Gxx[NX * NX], Gxu[NX * NU], Guu[NU * NU], gx[NX], gu[NU];
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            MMPC_UNROLL for (int j = i; j < NX; ++j) {
+                double a = H[tri(i, j, S)];
+                MMPC_UNROLL for (int l = 0; l < NX; ++l) a = fma(Fx[l * NX + i], PA[l * NX + j], a);
+                Gxx[i * NX + j] = a;
+                Gxx[j * NX + i] = a;
+            }
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+                double a = H[tri(i, NX + j, S)];
+                MMPC_UNROLL for (int l = 0; l < NX; ++l) a = fma(Fx[l * NX + i], PB[l * NU + j], a);
+                Gxu[i * NU + j] = a;
+            }
+            double a = qx[i];
+            MMPC_UNROLL for (int l = 0; l < NX; ++l) a = fma(Fx[l * NX + i], y[l], a);
+            gx[i] = a;
+        }
+        MMPC_UNROLL for (int i = 0; i < NU; ++i) {
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+                double a = (i <= j ? H[tri(NX + i, NX + j, S)] : H[tri(NX + j, NX + i, S)]) + V.Pvv[i * NU + j];
+                MMPC_UNROLL for (int l = 0; l < NX; ++l) {
+                    a = fma(Fu[l * NU + i], PB[l * NU + j], a);
+                    a = fma(V.Pxv[l * NU + i], Fu[l * NU + j], a);
+                }
+                Guu[i * NU + j] = a;
+            }
+            double a = qu[i] + yv[i];
+            MMPC_UNROLL for (int l = 0; l < NX; ++l) a = fma(Fu[l * NU + i], y[l], a);
+            gu[i] = a;
+        }
+        MMPC_UNROLL for (int i = 0; i < NU; ++i) MMPC_UNROLL for (int j = i + 1; j < NU; ++j) {  // symmetrise
+            const double a = 0.5 * (Guu[i * NU + j] + Guu[j * NU + i]);
+            Guu[i * NU + j] = Guu[j * NU + i] = a;
+        }
+        ok = chol<NU>(Guu) && ok;
+        // gains: Kx = -Guu^-1 Gxu', Kv = Guu^-1 (2R), k0 = -Guu^-1 gu
+        double Kx[NU * NX], Kv[NU * NU], k0[NU];
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            double col[NU];
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) col[j] = -Gxu[i * NU + j];
+            chol_solve<NU>(Guu, col);
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) Kx[j * NX + i] = col[j];
+        }
+        MMPC_UNROLL for (int l = 0; l < NU; ++l) {
+            double col[NU];
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) col[j] = (j == l) ? 2.0 * c.R[l] : 0.0;
+            chol_solve<NU>(Guu, col);
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) Kv[j * NU + l] = col[j];
+        }
+        MMPC_UNROLL for (int j = 0; j < NU; ++j) k0[j] = -gu[j];
+        chol_solve<NU>(Guu, k0);
+        // store gains and the value function of stage k+1 (needed by the forward sweep for lam_k)
+        MMPC_UNROLL for (int i = 0; i < NU * NX; ++i) c.st(c.W.KX, k * NU * NX + i, Kx[i]);
+        MMPC_UNROLL for (int i = 0; i < NU * NU; ++i) c.st(c.W.KV, k * NU * NU + i, Kv[i]);
+        MMPC_UNROLL for (int i = 0; i < NU; ++i) c.st(c.W.K0, k * NU + i, k0[i]);
+        MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) c.st(c.W.PXX, k * NX * NX + i, V.Pxx[i]);
+        MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) c.st(c.W.PXV, k * NX * NU + i, V.Pxv[i]);
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) c.st(c.W.PX, k * NX + i, V.px[i]);
+        // new value function
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            MMPC_UNROLL for (int j = i; j < NX; ++j) {
+                double a = Gxx[i * NX + j];
+                MMPC_UNROLL for (int l = 0; l < NU; ++l) a = fma(Gxu[i * NU + l], Kx[l * NX + j], a);
+                V.Pxx[i * NX + j] = a;
+                V.Pxx[j * NX + i] = a;
+            }
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+                double a = 0.0;
+                MMPC_UNROLL for (int l = 0; l < NU; ++l) a = fma(Gxu[i * NU + l], Kv[l * NU + j], a);
+                V.Pxv[i * NU + j] = a;
+            }
+            double a = gx[i];
+            MMPC_UNROLL for (int l = 0; l < NU; ++l) a = fma(Gxu[i * NU + l], k0[l], a);
+            V.px[i] = a;
+        }
+        MMPC_UNROLL for (int i = 0; i < NU; ++i) {
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) V.Pvv[i * NU + j] = (i == j ? 2.0 * c.R[i] : 0.0) - 2.0 * c.R[i] * Kv[i * NU + j];
+            V.pv[i] = qv[i] - 2.0 * c.R[i] * k0[i];
+        }
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) xn[i] = x[i];
+        if (k == N - 1) {  // stationarity w.r.t. x_N is -lam_{N-1}
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) nrm.dual_inf = fmax(nrm.dual_inf, fabs(lam[i]));
+        }
+    }
+    return ok;
+}
+
+// forward sweep: step, new multipliers, directional derivative of f, and merit pieces of the full step.
+template <class M>
+__device__ void forward_sweep(const SolveCtx<M>& c, double& gradf_d, double& lam_inf, double& f1, double& theta1, bool& finite) {
+    constexpr int NX = M::NX, NU = M::NU;
+    const int N = c.P.N;
+    double dx[NX], dv[NU], wq[NX];
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+        dx[i] = 0.0;
+        wq[i] = 2.0 * c.Q[i];
+    }
+    MMPC_UNROLL for (int j = 0; j < NU; ++j) dv[j] = 0.0;
+    gradf_d = 0.0; lam_inf = 0.0; f1 = 0.0; theta1 = 0.0; finite = true;
+    double x[NX];
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) x[i] = c.ld(c.W.X, i);
+    for (int k = 0; k < N; ++k) {
+        double u[NU], v[NU], r[NX], xn[NX];
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            r[i] = c.traj(k, i);
+            xn[i] = c.ld(c.W.X, (k + 1) * NX + i);
+        }
+        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+            u[j] = c.ld(c.W.U, k * NU + j);
+            v[j] = k ? c.ld(c.W.U, (k - 1) * NU + j) : c.uinit[j];
+        }
+        double F[NX], Fx[NX * NX], Fu[NX * NU];
+        c.template step<1>(x, u, nullptr, nullptr, nullptr, F, Fx, Fu, nullptr);
+        double du[NU];
+        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+            double a = c.ld(c.W.K0, k * NU + j);
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) a = fma(c.ld(c.W.KX, (k * NU + j) * NX + i), dx[i], a);
+            MMPC_UNROLL for (int l = 0; l < NU; ++l) a = fma(c.ld(c.W.KV, (k * NU + j) * NU + l), dv[l], a);
+            du[j] = a;
+            c.st(c.W.DU, k * NU + j, a);
+            finite = finite && isfinite(a);
+        }
+        double dxn[NX];
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            double a = F[i] - xn[i];
+            MMPC_UNROLL for (int j = 0; j < NX; ++j) a = fma(Fx[i * NX + j], dx[j], a);
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) a = fma(Fu[i * NU + j], du[j], a);
+            dxn[i] = a;
+            c.st(c.W.DX, (k + 1) * NX + i, a);
+            // directional derivative of e'Qe: 2 Q e . (Fx dx + Fu du) = 2 Q e . (dxn - c)
+            gradf_d = fma(wq[i] * (F[i] - r[i]), a - (F[i] - xn[i]), gradf_d);
+        }
+        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+            gradf_d = fma(2.0 * c.R[j] * (u[j] - v[j]), du[j] - dv[j], gradf_d);
+            gradf_d = fma(2.0 * c.Rm[j] * u[j], du[j], gradf_d);
+        }
+        // multiplier of g_k from the value function of stage k+1
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            double a = c.ld(c.W.PX, k * NX + i);
+            MMPC_UNROLL for (int j = 0; j < NX; ++j) a = fma(c.ld(c.W.PXX, (k * NX + i) * NX + j), dxn[j], a);
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) a = fma(c.ld(c.W.PXV, (k * NX + i) * NU + j), du[j], a);
+            c.st(c.W.LAMN, k * NX + i, a);
+            lam_inf = fmax(lam_inf, fabs(a));
+        }
+        // fused trial evaluation of the full step at node k
+        {
+            double xt[NX], ut[NU], Ft[NX];
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) xt[i] = x[i] + dx[i];
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) ut[j] = u[j] + du[j];
+            c.template step<0>(xt, ut, nullptr, nullptr, nullptr, Ft, nullptr, nullptr, nullptr);
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+                const double e = Ft[i] - r[i];
+                f1 = fma(c.Q[i] * e, e, f1);
+                theta1 += fabs(Ft[i] - (xn[i] + dxn[i]));
+            }
+            MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+                const double d = ut[j] - (v[j] + dv[j]);
+                f1 = fma(c.R[j] * d, d, f1);
+                f1 = fma(c.Rm[j] * ut[j], ut[j], f1);
+            }
+        }
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            x[i] = xn[i];
+            dx[i] = dxn[i];
+        }
+        MMPC_UNROLL for (int j = 0; j < NU; ++j) dv[j] = du[j];
+    }
+}
+
+// merit pieces at z + alpha dz
+template <class M>
+__device__ void trial_eval(const SolveCtx<M>& c, double alpha, double& f1, double& theta1) {
+    constexpr int NX = M::NX, NU = M::NU;
+    const int N = c.P.N;
+    f1 = 0.0; theta1 = 0.0;
+    double x[NX], v[NU];
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) x[i] = c.ld(c.W.X, i);
+    MMPC_UNROLL for (int j = 0; j < NU; ++j) v[j] = c.uinit[j];
+    for (int k = 0; k < N; ++k) {
+        double u[NU], xn[NX], F[NX];
+        MMPC_UNROLL for (int j = 0; j < NU; ++j) u[j] = fma(alpha, c.ld(c.W.DU, k * NU + j), c.ld(c.W.U, k * NU + j));
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) xn[i] = fma(alpha, c.ld(c.W.DX, (k + 1) * NX + i), c.ld(c.W.X, (k + 1) * NX + i));
+        c.template step<0>(x, u, nullptr, nullptr, nullptr, F, nullptr, nullptr, nullptr);
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            const double e = F[i] - c.traj(k, i);
+            f1 = fma(c.Q[i] * e, e, f1);
+            theta1 += fabs(F[i] - xn[i]);
+            x[i] = xn[i];
+        }
+        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+            const double d = u[j] - v[j];
+            f1 = fma(c.R[j] * d, d, f1);
+            f1 = fma(c.Rm[j] * u[j], u[j], f1);
+            v[j] = u[j];
+        }
+    }
+}
+
+template <class M>
+__global__ void __launch_bounds__(32) solve_kernel_t1(mmpc_problem P, mmpc_workspace W, mmpc_solve_io io) {
+    constexpr int NX = M::NX, NU = M::NU, S = NX + NU;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= W.B) return;
+    const int N = P.N;
+    SolveCtx<M> c(P, W, io, b);
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) c.Q[i] = c.ld(W.Qw, i);
+    MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+        c.R[j] = c.ld(W.Rw, j);
+        c.Rm[j] = c.ld(W.Rmw, j);
+        c.uinit[j] = io.control[(size_t)b * NU + j];
+    }
+    // ---- start point: warm = previous solution of this slot (ModelControl.cpp:161), else zeros (:28-50) ----
+    const bool warm = io.warm_start && W.have_warm;
+    if (!warm) {
+        for (int r = NX; r < (N + 1) * NX; ++r) c.st(W.X, r, 0.0);
+        for (int r = 0; r < N * NU; ++r) c.st(W.U, r, 0.0);
+    }
+    if (!(warm && io.warm_start_duals))
+        for (int r = 0; r < N * NX; ++r) c.st(W.LAM, r, 0.0);
+    double x0[NX];
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+        x0[i] = io.state[(size_t)b * NX + i];
+        c.st(W.X, i, x0[i]);  // x_0 pinned (ModelControl.cpp:144-145)
+    }
+    if (P.is_linear) {  // A, B, xdot at (state, control) (ModelControl.cpp:125-135), kept row-major
+        double xd[NX], A[NX * NX], Bm[NX * NU];
+        M::fAB(x0, c.uinit, xd, A, Bm);
+        MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) c.st(W.LIN, i, A[i]);
+        MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) c.st(W.LIN, NX * NX + i, Bm[i]);
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) c.st(W.LIN, NX * NX + NX * NU + i, xd[i]);
+    }
+    double nu_merit = 1.0, delta_last = 0.0, err = INFINITY, fval = 0.0;
+    int it = 0, status = MMPC_SOLVE_MAX_ITER, ls_total = 0, reg_total = 0;
+    const int nfree = N * S, ncon = N * NX;  // free variables: u_0, (x_k,u_k) k=1..N-1, x_N
+    for (it = 0;; ++it) {
+        SweepNorms nrm;
+        double delta = 0.0;
+        bool ok = backward_sweep<M>(c, delta, nrm);
+        // IPOPT scaled optimality error (Waechter & Biegler 2006 eq. 5) [upstream]: s_max = 100
+        const double sd = fmax(100.0, nrm.lam_l1 / (double)(nfree + ncon)) / 100.0;
+        err = fmax(nrm.dual_inf / sd, nrm.prim_inf);
+        fval = nrm.fval;
+        if (!isfinite(err)) { status = MMPC_SOLVE_NUMERICAL; break; }
+        if (err <= io.tol) { status = MMPC_SOLVE_CONVERGED; break; }
+        if (it >= io.max_iter) { status = MMPC_SOLVE_MAX_ITER; break; }
+        // inertia correction: retry the sweep with delta on the diagonal until every G_uu is PD
+        int tries = 0;
+        while (!ok && tries < 24) {
+            delta = (delta == 0.0) ? (delta_last > 0.0 ? fmax(1e-20, delta_last / 3.0) : 1e-4) : delta * 8.0;
+            SweepNorms dummy;
+            ok = backward_sweep<M>(c, delta, dummy);
+            ++tries; ++reg_total;
+        }
+        if (!ok) { status = MMPC_SOLVE_NUMERICAL; break; }
+        if (delta > 0.0) delta_last = delta;
+        double gd, lam_inf, f1, th1;
+        bool finite;
+        forward_sweep<M>(c, gd, lam_inf, f1, th1, finite);
+        if (!finite) { status = MMPC_SOLVE_NUMERICAL; break; }
+        nu_merit = fmax(nu_merit, 1.1 * lam_inf + 1e-8);
+        const double m0 = nrm.fval + nu_merit * nrm.theta;
+        const double D = gd - nu_merit * nrm.theta;
+        double alpha = 1.0;
+        for (int ls = 0; ls < 40; ++ls) {
+            if (f1 + nu_merit * th1 <= m0 + 1e-4 * alpha * D + 1e-12 * fabs(m0)) break;
+            alpha *= 0.5;
+            ++ls_total;
+            trial_eval<M>(c, alpha, f1, th1);
+        }
+        for (int r = NX; r < (N + 1) * NX; ++r) c.st(W.X, r, fma(alpha, c.ld(W.DX, r), c.ld(W.X, r)));
+        for (int r = 0; r < N * NU; ++r) c.st(W.U, r, fma(alpha, c.ld(W.DU, r), c.ld(W.U, r)));
+        for (int r = 0; r < N * NX; ++r) {
+            const double l = c.ld(W.LAM, r);
+            c.st(W.LAM, r, fma(alpha, c.ld(W.LAMN, r) - l, l));
+        }
+    }
+    // ---- outputs in the reference's V layout (ModelGenerator.cpp:76-112; unpacked ModelControl.cpp:174-190) ----
+    const int NV = NX * (N + 1) + NU * N;
+    double* Vb = io.V_out + (size_t)b * NV;
+    for (int k = 0; k <= N; ++k) {
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) Vb[k * S + i] = c.ld(W.X, k * NX + i);
+        if (k < N) MMPC_UNROLL for (int j = 0; j < NU; ++j) Vb[k * S + NX + j] = c.ld(W.U, k * NU + j);
+    }
+    if (io.lam_out)
+        for (int r = 0; r < N * NX; ++r) io.lam_out[(size_t)b * N * NX + r] = c.ld(W.LAM, r);
+    if (io.stats) {
+        mmpc_stats s;
+        s.objective = fval; s.kkt_error = err; s.mu = 0.0; s.iterations = it; s.status = status;
+        s.ls_steps = ls_total; s.reg_steps = reg_total;
+        io.stats[b] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers + vtable
+// ---------------------------------------------------------------------------------------------
+template <class M>
+struct Launch {
+    static cudaError_t eval_nodes(const mmpc_problem& P, long long n, const double* x, const double* u, const double* xn,
+                                  const double* w, double* g, double* Fx, double* Fu, double* H, cudaStream_t st, int* launches) {
+        if (P.integrator != MMPC_EULER || P.is_linear) return cudaErrorNotSupported;
+        if (n <= 0) return cudaSuccess;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long want = (n + 127) / 128;
+        const int grid = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);  // grid-stride, multiple of the SM count
+        if (w) eval_nodes_kernel<M, true><<<grid, 128, 0, st>>>(P.h, n, x, u, xn, w, g, Fx, Fu, H);
+        else eval_nodes_kernel<M, false><<<grid, 128, 0, st>>>(P.h, n, x, u, xn, w, g, Fx, Fu, H);
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
+    static cudaError_t linearise(int n, const double* x, const double* u, double* xdot, double* A, double* B, cudaStream_t st,
+                                 int* launches) {
+        if (n <= 0) return cudaSuccess;
+        linearise_kernel<M><<<(n + 127) / 128, 128, 0, st>>>(n, x, u, xdot, A, B);
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
+    static cudaError_t nlp_eval(const mmpc_problem& P, int B, const double* V, const double* p, const double* lam, double lam_f,
+                                double* f, double* g, double* grad_f, double* Fx, double* Fu, double* Hzz, cudaStream_t st,
+                                int* launches) {
+        if (P.integrator != MMPC_EULER) return cudaErrorNotSupported;
+        if (B <= 0) return cudaSuccess;
+        const int NV = M::NX * (P.N + 1) + M::NU * P.N;
+        cudaError_t e;
+        if (f && (e = cudaMemsetAsync(f, 0, sizeof(double) * B, st)) != cudaSuccess) return e;
+        if (grad_f && (e = cudaMemsetAsync(grad_f, 0, sizeof(double) * (size_t)B * NV, st)) != cudaSuccess) return e;
+        dim3 grid((P.N + 127) / 128, B);
+        nlp_eval_kernel<M><<<grid, 128, 0, st>>>(P, B, V, p, lam, lam_f, f, g, grad_f, Fx, Fu, Hzz);
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
+    static cudaError_t solve(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st, int* launches) {
+        if (P.integrator != MMPC_EULER || P.bounded) return cudaErrorNotSupported;
+        solve_kernel_t1<M><<<(W.B + 31) / 32, 32, 0, st>>>(P, W, io);
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
+};
+
+}  // namespace mmpc
+
+// Defines `mmpc_vtable_<MODEL>()` for the generated functor `mmpc_model_<MODEL>`.
+#define MMPC_DEFINE_MODEL(MODEL)                                                                                         \
+    extern "C" const mmpc_model_vtable* mmpc_vtable_##MODEL(void) {                                                       \
+        using M = mmpc_model_##MODEL;                                                                                     \
+        static const mmpc_model_vtable vt = {MMPC_VTABLE_VERSION, M::MODEL_NAME, M::NX, M::NU,                            \
+                                             {M::OPS_F, M::TRANS_F, M::OPS_FAB, M::TRANS_FAB, M::OPS_FABH, M::TRANS_FABH}, \
+                                             &mmpc::Launch<M>::eval_nodes, &mmpc::Launch<M>::linearise,                   \
+                                             &mmpc::Launch<M>::nlp_eval, &mmpc::Launch<M>::solve};                        \
+        return &vt;                                                                                                       \
+    }
+// Additionally exports the generic entry point a stand-alone generated model library is dlopen'ed by
+// (the role `nlpsol("nlpsol","ipopt",dll,...)` plays at ModelControl.cpp:61-62).
+#define MMPC_EXPORT_MODEL_ENTRY(MODEL) \
+    extern "C" const mmpc_model_vtable* mmpc_model_vtable_get(void) { return mmpc_vtable_##MODEL(); }

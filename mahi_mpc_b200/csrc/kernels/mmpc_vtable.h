@@ -1,0 +1,74 @@
+// mahi-mpc-b200 :: internal interface between the core library (csrc/abi) and a model's kernel set
+// (one translation unit per model, produced by the ModelGenerator: generated model functor +
+// mmpc_kernels.cuh + MMPC_DEFINE_MODEL).  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#define MMPC_MAXNX 16
+#define MMPC_MAXNU 8
+#define MMPC_VTABLE_VERSION 3
+
+struct mmpc_stats;  // public struct (include/mahi_mpc_b200.h)
+
+// Problem constants shared by every instance of a batch (passed to kernels by value).
+struct mmpc_problem {
+    int N;           // shooting nodes
+    int is_linear;   // F_lin instead of F (ModelGenerator.cpp:47-48,58)
+    int integrator;  // MMPC_EULER / MMPC_RK4
+    int substeps;
+    double h;        // step_size in seconds
+    int bounded;     // any finite bound present
+    double x_min[MMPC_MAXNX], x_max[MMPC_MAXNX], u_min[MMPC_MAXNU], u_max[MMPC_MAXNU];
+};
+
+// Device workspace of one solver handle. Iterates are structure-of-arrays with the instance index
+// fastest: element (row r, instance b) of an array with `rows` rows lives at [r * Bp + b].
+struct mmpc_workspace {
+    int B, Bp;
+    // iterate (persists between solves = warm start)
+    double *X;     // (N+1)*nx rows : x_k[i] at row k*nx+i
+    double *U;     // N*nu rows
+    double *LAM;   // N*nx rows     : multiplier of g_k
+    double *ZLU, *ZUU, *ZLX, *ZUX;  // bound multipliers for u (N*nu rows) and x_1..x_N (N*nx rows)
+    // Newton step
+    double *DX, *DU, *LAMN, *DZLU, *DZUU, *DZLX, *DZUX;
+    // Riccati products per stage
+    double *KX;    // N*nu*nx rows : feedback on dx
+    double *KV;    // N*nu*nu rows : feedback on du_{k-1}
+    double *K0;    // N*nu rows    : feed-forward
+    double *PXX;   // N*nx*nx rows : value-function Hessian blocks of stage k+1 (stored at k)
+    double *PXV;   // N*nx*nu rows
+    double *PX;    // N*nx rows
+    // linearisation data for is_linear models (nx*nx + nx*nu + nx rows)
+    double *LIN;
+    // weights, SoA: Q nx rows, R nu rows, Rm nu rows
+    double *Qw, *Rw, *Rmw;
+    int have_warm;  // X/U (and LAM) hold a previous solution
+};
+
+struct mmpc_solve_io {
+    const double *state, *control, *traj;  // AoS device pointers (B*nx, B*nu, B*N*nx)
+    double *V_out, *lam_out;               // AoS device pointers (B*NV, B*M); lam_out may be null
+    mmpc_stats* stats;                     // device pointer (B) or null
+    double tol, mu_init;
+    int max_iter, warm_start, warm_start_duals, variant;
+};
+
+struct mmpc_model_vtable {
+    int version;
+    const char* name;
+    int nx, nu;
+    int op_counts[6];
+    // launches return cudaError_t of the launch; *launches += number of kernels launched
+    cudaError_t (*eval_nodes)(const mmpc_problem& P, long long n, const double* x, const double* u, const double* xn,
+                              const double* w, double* g, double* Fx, double* Fu, double* H, cudaStream_t st, int* launches);
+    cudaError_t (*linearise)(int n, const double* x, const double* u, double* xdot, double* A, double* B, cudaStream_t st,
+                             int* launches);
+    cudaError_t (*nlp_eval)(const mmpc_problem& P, int B, const double* V, const double* p, const double* lam, double lam_f,
+                            double* f, double* g, double* grad_f, double* Fx, double* Fu, double* Hzz, cudaStream_t st,
+                            int* launches);
+    cudaError_t (*solve)(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st,
+                         int* launches);
+};
+
+extern "C" typedef const mmpc_model_vtable* (*mmpc_vtable_getter)(void);

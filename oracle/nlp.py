@@ -474,9 +474,6 @@ def synthetic_batch(nx, nu, N, h, B, seed=0x5EED, offset=0):
     s, c = np.sin(arg), np.cos(arg)
     traj = np.empty((B, N, nx))
     for j in range(nx):
-        sign = 1.0 if (j % half if j >= half else j) % 2 == 0 else -1.0
-        if j < half:
-            traj[:, :, j] = sign * amp[:, None] * s
-        else:
-            traj[:, :, j] = sign * amp[:, None] * 2 * np.pi * frq[:, None] * c
+        sign = 1.0 if ((j - half) if j >= half else j) % 2 == 0 else -1.0
+        traj[:, :, j] = sign * amp[:, None] * (s if j < half else 2 * np.pi * frq[:, None] * c)
     return x0, np.zeros((B, nu)), traj

@@ -1,0 +1,262 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle and the golden
+fixtures.  Tolerances are north_star's: 1e-12 relative for rollout/Jacobian/Hessian evaluations,
+1e-6 on controls and 1e-8 relative on the objective for converged solves."""
+import numpy as np
+import pytest
+
+from oracle import nlp
+
+pytestmark = pytest.mark.gpu
+
+EVAL_RTOL = 1e-12   # north_star: "within 1e-12 relative error in fp64"
+U_ATOL = 1e-6       # north_star: "within 1e-6 on controls"
+OBJ_RTOL = 1e-8     # north_star: "1e-8 relative on the objective"
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(1.0, np.abs(b).max())
+
+
+@pytest.fixture(scope="module")
+def api(native_lib):
+    from mahi_mpc_b200 import api as a
+    assert a.device_count() >= 1
+    return a
+
+
+def random_nodes(n, seed):
+    rng = np.random.default_rng(seed)
+    x = np.c_[rng.uniform(-np.pi, np.pi, (n, 2)), rng.uniform(-5, 5, (n, 2))]
+    u = rng.uniform(-10, 10, (n, 2))
+    xn = rng.uniform(-3, 3, (n, 4))
+    w = rng.uniform(-2, 2, (n, 4))
+    return x, u, xn, w
+
+
+def test_eval_nodes_vs_golden(api, golden):
+    g_ = golden["nodes"]
+    x, u, w = np.array(g_["x"]), np.array(g_["u"]), np.array(g_["w"])
+    n = x.shape[0]
+    h = 0.002
+    m = api.Model("double_pendulum", N=25)
+    xn = np.zeros_like(x)
+    g, Fx, Fu, H = m.eval_nodes(x.T.copy(), u.T.copy(), xn.T.copy(), w.T.copy())
+    f_gpu = (g.T - x) / h
+    A_gpu = (Fx.T.reshape(n, 4, 4) - np.eye(4)) / h
+    B_gpu = Fu.T.reshape(n, 4, 2) / h
+    for src in ("ref_old", "mp"):  # the reference's own closed forms, and 50-digit mpmath
+        assert rel(f_gpu, g_[src]["f"]) < 5e-12  # (g - x)/h amplifies rounding of x + h f by 1/h
+        assert rel(A_gpu, g_[src]["A"]) < 5e-12
+        assert rel(B_gpu, g_[src]["B"]) < 5e-12
+    Hm = np.array(g_["mp"]["Hc"])
+    Hu = np.array([[Hm[i, a, b] for a in range(6) for b in range(a, 6)] for i in range(n)])
+    assert rel(H.T / h, Hu) < EVAL_RTOL
+    # known answers: f(0,0) = [0,0,-9.81,9.81]; B(0,0) rows 2,3 = [[1,-2],[-2,5]]
+    np.testing.assert_allclose(f_gpu[0], g_["known"]["f00"], atol=1e-12)
+    np.testing.assert_allclose(B_gpu[0][2:], g_["known"]["B00_rows23"], atol=1e-12)
+    np.testing.assert_allclose(f_gpu[1][2:], g_["known"]["qdd_survey"], rtol=1e-11)
+
+
+@pytest.mark.parametrize("n", [1, 31, 4097, 200_000])
+def test_eval_nodes_vs_oracle(api, coracle, n):
+    x, u, xn, w = random_nodes(n, 100 + n)
+    m = api.Model("double_pendulum", N=25)
+    g, Fx, Fu, H = m.eval_nodes(x.T.copy(), u.T.copy(), xn.T.copy(), w.T.copy())
+    go, Fxo, Fuo, Ho = coracle.node_eval("double_pendulum", m.h, x, u, xn, w)
+    assert rel(g.T, go) < EVAL_RTOL
+    assert rel(Fx.T.reshape(n, 4, 4), Fxo) < EVAL_RTOL
+    assert rel(Fu.T.reshape(n, 4, 2), Fuo) < EVAL_RTOL
+    iu = np.triu_indices(6)
+    assert rel(H.T, Ho[:, iu[0], iu[1]]) < EVAL_RTOL
+    # without w: H untouched, same g/Fx/Fu
+    g2, Fx2, Fu2, H2 = m.eval_nodes(x.T.copy(), u.T.copy(), xn.T.copy())
+    assert H2 is None and np.array_equal(g2, g) and np.array_equal(Fx2, Fx)
+
+
+def test_eval_nodes_empty(api):
+    m = api.Model("double_pendulum", N=25)
+    z = np.zeros((4, 0))
+    g, Fx, Fu, H = m.eval_nodes(z, np.zeros((2, 0)), z)
+    assert g.shape == (4, 0)
+
+
+def test_linearise_vs_oracle(api, coracle):
+    x, u, _, _ = random_nodes(257, 5)
+    m = api.Model("double_pendulum", N=25)
+    xd, A, B = m.linearise(x, u)
+    for i in (0, 100, 256):
+        f, Ac, Bc = coracle.linearise("double_pendulum", x[i], u[i])
+        assert rel(xd[i], f) < EVAL_RTOL and rel(A[i], Ac) < EVAL_RTOL and rel(B[i], Bc) < EVAL_RTOL
+
+
+@pytest.mark.parametrize("N,is_linear", [(1, False), (10, False), (25, True), (50, False), (200, False)])
+def test_nlp_eval_vs_oracle(api, coracle, N, is_linear):
+    rng = np.random.default_rng(N)
+    B = 5
+    P = nlp.Problem(N=N, is_linear=is_linear)
+    m = api.Model("double_pendulum", N=N, is_linear=is_linear)
+    assert (m.NV, m.M, m.np) == (P.NV, P.M, P.np_)
+    Q, R, Rm = nlp.default_weights(4, 2)
+    x0, _, traj = nlp.synthetic_batch(4, 2, N, P.h, B)
+    ps = []
+    for b in range(B):
+        ui = rng.uniform(-1, 1, 2)
+        ps.append(P.pack_p(traj[b], Q, R, Rm, ui, P.linearisation(x0[b], ui) if is_linear else None))
+    p = np.stack(ps)
+    V = rng.uniform(-0.5, 0.5, (B, P.NV))
+    lam = rng.uniform(-2, 2, (B, P.M))
+    out = m.nlp_eval(V, p, lam, lam_f=0.7)
+    for b in range(B):
+        o = coracle.nlp_eval("double_pendulum", N, P.h, is_linear, V[b], p[b], lam[b], 0.7)
+        assert abs(out["f"][b] - o["f"]) <= EVAL_RTOL * abs(o["f"])
+        assert rel(out["g"][b], o["g"]) < EVAL_RTOL
+        assert rel(out["grad_f"][b], o["grad_f"]) < EVAL_RTOL
+        assert rel(out["Fx"][b], o["Fx"]) < EVAL_RTOL
+        assert rel(out["Fu"][b], o["Fu"]) < EVAL_RTOL
+        assert rel(out["Hzz"][b], o["Hzz"]) < EVAL_RTOL
+    # numpy oracle (dense jac / hess in the reference's CCS-able layout) on instance 0
+    f, gf = P.nlp_grad_f(V[0], p[0])
+    _, J = P.nlp_jac_g(V[0], p[0])
+    H = P.nlp_hess_l(V[0], p[0], 0.7, lam[0])
+    s = 6
+    for k in range(N):
+        assert rel(out["Fx"][0, k], J[k * 4:(k + 1) * 4, k * s:k * s + 4]) < EVAL_RTOL
+        assert rel(out["Fu"][0, k], J[k * 4:(k + 1) * 4, k * s + 4:(k + 1) * s]) < EVAL_RTOL
+        assert rel(out["Hzz"][0, k], H[k * s:(k + 1) * s, k * s:(k + 1) * s]) < EVAL_RTOL
+    assert rel(out["grad_f"][0], gf) < EVAL_RTOL
+
+
+def _solve_inputs(N, B, seed_offset=0):
+    P = nlp.Problem(N=N)
+    Q, R, Rm = nlp.default_weights(4, 2)
+    x0, up, traj = nlp.synthetic_batch(4, 2, N, P.h, B, offset=seed_offset)
+    p = np.stack([P.pack_p(traj[b], Q, R, Rm, up[b]) for b in range(B)])
+    return P, (Q, R, Rm), x0, up, traj, p
+
+
+def test_solve_vs_golden(api, golden):
+    gs = golden["solves"]
+    for case in gs["cases"]:
+        if case["u_bound"]:
+            continue
+        N = case["N"]
+        P = nlp.Problem(N=N)
+        pv = P.split_p(np.array(case["p"]))
+        m = api.Model("double_pendulum", N=N)
+        s = api.Solver(m, 1, tol=1e-10)
+        s.set_weights(pv["Q"], pv["R"], pv["Rm"])
+        V, lam, st = s.solve(np.array(case["x0"])[None], pv["u_init"][None].copy(), pv["r"][None].copy())
+        assert st["status"][0] == 0
+        Vg = np.array(case["V"])
+        Ug = Vg[:N * 6].reshape(N, 6)[:, 4:]
+        U = V[0, :N * 6].reshape(N, 6)[:, 4:]
+        assert np.abs(U - Ug).max() < U_ATOL
+        assert np.abs(V[0] - Vg).max() < U_ATOL
+        assert abs(st["objective"][0] - case["f"]) <= OBJ_RTOL * abs(case["f"])
+        assert rel(lam[0], case["lam_g"]) < 1e-6
+
+
+@pytest.mark.parametrize("N,B", [(10, 7), (25, 33), (50, 64), (100, 8), (200, 4)])
+def test_solve_vs_oracle(api, coracle, N, B):
+    P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B)
+    m = api.Model("double_pendulum", N=N)
+    s = api.Solver(m, B, tol=1e-10)
+    s.set_weights(Q, R, Rm)
+    V, lam, st = s.solve(x0, up, traj)
+    Vo, lamo, sto, bad = coracle.solve_batch("double_pendulum", N, P.h, False, x0, p, tol=1e-10)
+    assert bad == 0 and (st["status"] == 0).all()
+    s6 = 6
+    U = V[:, :N * s6].reshape(B, N, s6)[:, :, 4:]
+    Uo = Vo[:, :N * s6].reshape(B, N, s6)[:, :, 4:]
+    assert np.abs(U - Uo).max() < U_ATOL
+    assert np.abs(V - Vo).max() < U_ATOL
+    assert (np.abs(st["objective"] - sto["f"]) <= OBJ_RTOL * np.abs(sto["f"])).all()
+    # the returned point satisfies the KKT conditions as judged by the ORACLE's evaluator
+    for b in range(min(B, 4)):
+        o = coracle.nlp_eval("double_pendulum", N, P.h, False, V[b], p[b], lam[b], 1.0)
+        assert np.abs(o["g"]).max() < 1e-9
+        # stationarity: grad_f + J' lam = 0 on the free variables
+        r = o["grad_f"].copy()
+        for k in range(N):
+            r[k * s6:k * s6 + 4] += o["Fx"][k].T @ lam[b, k * 4:(k + 1) * 4]
+            r[k * s6 + 4:(k + 1) * s6] += o["Fu"][k].T @ lam[b, k * 4:(k + 1) * 4]
+            r[(k + 1) * s6:(k + 1) * s6 + 4] -= lam[b, k * 4:(k + 1) * 4]
+        assert np.abs(r[4:]).max() < 1e-7
+
+
+def test_solve_reference_tolerance_and_warm_start(api, coracle):
+    """tol = 1e-5 (ModelControl.cpp:54): still inside the north_star ball of the tight solution; the second
+    call starts from the previous solution (ModelControl.cpp:161) and needs fewer iterations."""
+    N, B = 50, 128
+    P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B, seed_offset=1000)
+    m = api.Model("double_pendulum", N=N)
+    s = api.Solver(m, B)  # reference defaults: tol 1e-5, max_iter 200
+    s.set_weights(Q, R, Rm)
+    V, lam, st = s.solve(x0, up, traj)
+    Vo, _, sto, bad = coracle.solve_batch("double_pendulum", N, P.h, False, x0, p, tol=1e-11)
+    assert bad == 0 and (st["status"] == 0).all()
+    assert np.abs(V - Vo).max() < U_ATOL
+    assert (np.abs(st["objective"] - sto["f"]) <= OBJ_RTOL * np.abs(sto["f"])).all()
+    it_cold = st["iterations"].copy()
+    V2, _, st2 = s.solve(x0, up, traj)
+    assert (st2["iterations"] <= 1).all() and (it_cold >= 2).all()
+    assert np.abs(V2 - V).max() < 1e-6
+    s.reset_warm_start()
+    V3, _, st3 = s.solve(x0, up, traj)
+    assert np.array_equal(st3["iterations"], it_cold) and np.array_equal(V3, V)
+
+
+def test_solve_device_pointers_match_host(api):
+    import torch
+    N, B = 25, 40
+    P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B, seed_offset=50)
+    m = api.Model("double_pendulum", N=N)
+    s = api.Solver(m, B, tol=1e-9, warm_start=0)
+    s.set_weights(Q, R, Rm)
+    V, lam, st = s.solve(x0, up, traj)
+    dev = torch.device("cuda:0")
+    Vt, lamt, stt = s.solve(torch.from_numpy(x0).to(dev), torch.from_numpy(up).to(dev), torch.from_numpy(traj).to(dev))
+    torch.cuda.synchronize()
+    assert np.array_equal(Vt.cpu().numpy(), V) and np.array_equal(lamt.cpu().numpy(), lam)
+    st2 = api.stats_from_tensor(stt)
+    assert np.array_equal(st2["iterations"], st["iterations"])
+
+
+def test_solve_full_size_properties(api):
+    """BASELINE config 2 size (B=4096, N=50): size-independent checks -- every instance converged, continuity
+    holds, x_0 is pinned, shards reproduce the un-sharded result bit for bit, and re-solving from the solution is
+    a fixed point."""
+    N, B = 50, 4096
+    P, (Q, R, Rm), x0, up, traj, _ = _solve_inputs(N, B)
+    m = api.Model("double_pendulum", N=N)
+    s = api.Solver(m, B, warm_start=0)
+    s.set_weights(Q, R, Rm)
+    V, lam, st = s.solve(x0, up, traj)
+    assert (st["status"] == 0).all() and (st["kkt_error"] <= 1e-5).all()
+    assert np.array_equal(V[:, :4], x0)
+    out = m.nlp_eval(V[:64], np.stack([P.pack_p(traj[b], Q, R, Rm, up[b]) for b in range(64)]), lam[:64], want=("f", "g"))
+    assert np.abs(out["g"]).max() < 1e-5
+    assert rel(out["f"], st["objective"][:64]) < 1e-12
+    # shard [1024, 2048) solved alone == the same rows of the full batch
+    s2 = api.Solver(m, 1024, warm_start=0)
+    s2.set_weights(Q, R, Rm)
+    Vs, _, _ = s2.solve(x0[1024:2048].copy(), up[1024:2048].copy(), traj[1024:2048].copy())
+    assert np.array_equal(Vs, V[1024:2048])
+
+
+def test_solve_per_instance_weights_and_errors(api):
+    N, B = 10, 3
+    P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B)
+    m = api.Model("double_pendulum", N=N)
+    s = api.Solver(m, B, tol=1e-10)
+    Qb = np.stack([Q, 2 * Q, 0.5 * Q]); Rb = np.stack([R, R, 3 * R]); Rmb = np.stack([Rm, 2 * Rm, Rm])
+    s.set_weights(Qb, Rb, Rmb, per_instance=True)
+    V, _, st = s.solve(x0, up, traj)
+    for b in range(B):
+        pb = P.pack_p(traj[b], Qb[b], Rb[b], Rmb[b], up[b])
+        r = nlp.solve(P, x0[b], pb, tol=1e-11)
+        assert np.abs(V[b] - r.V).max() < U_ATOL and abs(st["objective"][b] - r.f) <= OBJ_RTOL * abs(r.f)
+    with pytest.raises(api.MmpcError):
+        api.Solver(m, 0)
+    with pytest.raises(api.MmpcError):
+        api.Model("no_such_model", N=5, nx=3, nu=1)
