@@ -139,7 +139,9 @@ def _stream_of(*arrs):
     for a in arrs:
         if _is_torch(a) and a.is_cuda:
             import torch
-            return C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream), a.device.index or 0
+            # torch's default stream is the legacy NULL stream; the ABI reads NULL as "the handle's own
+            # stream", so name it explicitly (cudaStreamLegacy == (cudaStream_t)0x1)
+            return C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream or 1), a.device.index or 0
     return None, None
 
 
