@@ -261,7 +261,8 @@ struct RiccatiState {
     double Pxx[M::NX * M::NX], Pxv[M::NX * M::NU], Pvv[M::NU * M::NU], px[M::NX], pv[M::NU];
 };
 
-// in-place Cholesky of the NU x NU matrix G (full storage, lower triangle used). returns false if not PD.
+// in-place Cholesky of the NU x NU matrix G (full storage, lower triangle used); the diagonal holds 1/l_jj so
+// the solves multiply instead of divide. returns false if not PD.
 template <int NU>
 __device__ __forceinline__ bool chol(double* G) {
     bool ok = true;
@@ -269,8 +270,8 @@ __device__ __forceinline__ bool chol(double* G) {
         double d = G[j * NU + j];
         MMPC_UNROLL for (int k = 0; k < NU; ++k) if (k < j) d = fma(-G[j * NU + k], G[j * NU + k], d);
         ok = ok && (d > 0.0) && isfinite(d);
-        const double l = sqrt(d > 0.0 ? d : 1.0), il = 1.0 / l;
-        G[j * NU + j] = l;
+        const double il = rsqrt(d > 0.0 ? d : 1.0);
+        G[j * NU + j] = il;
         MMPC_UNROLL for (int i = 0; i < NU; ++i) if (i > j) {
             double s = G[i * NU + j];
             MMPC_UNROLL for (int k = 0; k < NU; ++k) if (k < j) s = fma(-G[i * NU + k], G[j * NU + k], s);
@@ -285,12 +286,12 @@ __device__ __forceinline__ void chol_solve(const double* L, double* b) {
     MMPC_UNROLL for (int i = 0; i < NU; ++i) {
         double s = b[i];
         MMPC_UNROLL for (int k = 0; k < NU; ++k) if (k < i) s = fma(-L[i * NU + k], b[k], s);
-        b[i] = s / L[i * NU + i];
+        b[i] = s * L[i * NU + i];
     }
     MMPC_UNROLL for (int i = NU - 1; i >= 0; --i) {
         double s = b[i];
         MMPC_UNROLL for (int k = 0; k < NU; ++k) if (k > i) s = fma(-L[k * NU + i], b[k], s);
-        b[i] = s / L[i * NU + i];
+        b[i] = s * L[i * NU + i];
     }
 }
 
@@ -733,6 +734,10 @@ __global__ void __launch_bounds__(32) solve_kernel_t1(mmpc_problem P, mmpc_works
     }
 }
 
+}  // namespace mmpc
+#include "mmpc_solve_t2.cuh"
+namespace mmpc {
+
 // ---------------------------------------------------------------------------------------------
 // host-side launchers + vtable
 // ---------------------------------------------------------------------------------------------
@@ -775,8 +780,9 @@ struct Launch {
     }
     static cudaError_t solve(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st, int* launches) {
         if (P.integrator != MMPC_EULER || P.bounded) return cudaErrorNotSupported;
-        solve_kernel_t1<M><<<(W.B + 31) / 32, 32, 0, st>>>(P, W, io);
         if (launches) ++*launches;
+        if (W.variant == 2) return LaunchT2<M>::run(P, W, io, st);
+        solve_kernel_t1<M><<<(W.B + 31) / 32, 32, 0, st>>>(P, W, io);
         return cudaGetLastError();
     }
 };

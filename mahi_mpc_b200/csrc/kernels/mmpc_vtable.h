@@ -44,6 +44,18 @@ struct mmpc_workspace {
     // weights, SoA: Q nx rows, R nu rows, Rm nu rows
     double *Qw, *Rw, *Rmw;
     int have_warm;  // X/U (and LAM) hold a previous solution
+    // ---- variant T2 (sub-warp cooperative kernel): instance-major (AoS) arrays ----
+    double *V2;     // B * NV   iterate in the reference's V layout (persists = warm start)
+    double *LAM2;   // B * M
+    double *ZL2, *ZU2;  // B * NV  bound multipliers in V layout
+    double *DV2;    // B * NV   Newton step in V layout
+    double *LAMN2;  // B * M    multipliers of the QP
+    double *DZL2, *DZU2;  // B * NV
+    double *FG2;    // B * N * (nx*nx + nx*nu + nx + nx+2nu)   Fx, Fu, c, objective-gradient pieces of every node
+    double *KG2;    // B * N * (nu*(nx+nu) + nu)               feedback gains
+    double *PG2;    // B * N * (nx*(nx+nu+1))                  rows of the value function needed for lam
+    double *LIN2;   // B * (nx*nx + nx*nu + nx)
+    int variant;    // kernel variant the persistent state belongs to (1 = T1, 2 = T2)
 };
 
 struct mmpc_solve_io {

@@ -156,11 +156,12 @@ def test_solve_vs_golden(api, golden):
         assert rel(lam[0], case["lam_g"]) < 1e-6
 
 
-@pytest.mark.parametrize("N,B", [(10, 7), (25, 33), (50, 64), (100, 8), (200, 4)])
-def test_solve_vs_oracle(api, coracle, N, B):
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("N,B", [(1, 3), (10, 7), (25, 33), (50, 64), (100, 8), (200, 4)])
+def test_solve_vs_oracle(api, coracle, N, B, variant):
     P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B)
     m = api.Model("double_pendulum", N=N)
-    s = api.Solver(m, B, tol=1e-10)
+    s = api.Solver(m, B, tol=1e-10, kernel_variant=variant)
     s.set_weights(Q, R, Rm)
     V, lam, st = s.solve(x0, up, traj)
     Vo, lamo, sto, bad = coracle.solve_batch("double_pendulum", N, P.h, False, x0, p, tol=1e-10)

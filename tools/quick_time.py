@@ -23,4 +23,4 @@ for i in range(5):
     tm = s.last_timing()
     print(f"N={N} B={B} var={variant} wall {1e3*(t1-t0):.3f} ms  kernel {tm['kernel_ms']:.3f} ms  h2d {tm['h2d_ms']:.3f} d2h {tm['d2h_ms']:.3f}  "
           f"iters {st['iterations'].min()}-{st['iterations'].max()} mean {st['iterations'].mean():.2f} conv {(st['status']==0).mean():.3f} "
-          f"-> {B/tm['kernel_ms']*1e3:.3e} solves/s (kernel)")
+          f"ls {st['ls_steps'].sum()} reg {st['reg_steps'].sum()} -> {B/tm['kernel_ms']*1e3:.3e} solves/s (kernel)")
