@@ -295,446 +295,8 @@ __device__ __forceinline__ void chol_solve(const double* L, double* b) {
     }
 }
 
-template <class M>
-struct SolveCtx {
-    static constexpr int NX = M::NX, NU = M::NU, S = NX + NU, NH = S * (S + 1) / 2;
-    const mmpc_problem& P;
-    const mmpc_workspace& W;
-    const mmpc_solve_io& io;
-    int b;        // instance
-    size_t Bp;
-    double Q[NX], R[NU], Rm[NU], uinit[NU];
-    // linear-mode data (row-major A,B)
-    __device__ SolveCtx(const mmpc_problem& P_, const mmpc_workspace& W_, const mmpc_solve_io& io_, int b_)
-        : P(P_), W(W_), io(io_), b(b_), Bp(W_.Bp) {}
-    __device__ __forceinline__ double ld(const double* a, int row) const { return a[(size_t)row * Bp + b]; }
-    __device__ __forceinline__ void st(double* a, int row, double v) const { a[(size_t)row * Bp + b] = v; }
-    __device__ __forceinline__ double traj(int k, int i) const { return io.traj[((size_t)b * P.N + k) * NX + i]; }
-
-    // evaluate one node at (x,u) with the model or its linearisation
-    template <int WANT>
-    __device__ __forceinline__ void step(const double* x, const double* u, const double* wq, const double* r, const double* lam,
-                                         double* F, double* Fx, double* Fu, double* Hs) const {
-        if (P.is_linear) {
-            double A[NX * NX], Bm[NX * NU], xd0[NX], x0[NX];
-            MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) A[i] = ld(W.LIN, i);
-            MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) Bm[i] = ld(W.LIN, NX * NX + i);
-            MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-                xd0[i] = ld(W.LIN, NX * NX + NX * NU + i);
-                x0[i] = ld(W.X, i);  // x_init = pinned state (ModelControl.cpp:134)
-            }
-            step_linear<M, WANT>(P.h, x, u, A, Bm, xd0, x0, uinit, F, Fx, Fu, Hs);
-        } else {
-            step_euler<M, WANT>(P.h, x, u, wq, r, lam, F, Fx, Fu, Hs);
-        }
-    }
-};
-
-struct SweepNorms {
-    double dual_inf, prim_inf, theta, fval, lam_l1;
-};
-
-// backward sweep; returns false if some G_uu was not positive definite (caller regularises and retries)
-template <class M>
-__device__ bool backward_sweep(const SolveCtx<M>& c, double delta, SweepNorms& nrm) {
-    constexpr int NX = M::NX, NU = M::NU, S = NX + NU, NH = S * (S + 1) / 2;
-    const int N = c.P.N;
-    RiccatiState<M> V;
-    MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) V.Pxx[i] = 0.0;
-    MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) V.Pxv[i] = 0.0;
-    MMPC_UNROLL for (int i = 0; i < NU * NU; ++i) V.Pvv[i] = 0.0;
-    MMPC_UNROLL for (int i = 0; i < NX; ++i) V.px[i] = 0.0;
-    MMPC_UNROLL for (int i = 0; i < NU; ++i) V.pv[i] = 0.0;
-    double wq[NX];
-    MMPC_UNROLL for (int i = 0; i < NX; ++i) wq[i] = 2.0 * c.Q[i];
-    double du_next[NU];  // R-weighted control increment of stage k+1 (enters the u_k stationarity residual)
-    MMPC_UNROLL for (int j = 0; j < NU; ++j) du_next[j] = 0.0;
-    double xn[NX], lam_next_unused = 0.0;
-    (void)lam_next_unused;
-    MMPC_UNROLL for (int i = 0; i < NX; ++i) xn[i] = c.ld(c.W.X, N * NX + i);
-    nrm.dual_inf = nrm.prim_inf = nrm.theta = nrm.fval = nrm.lam_l1 = 0.0;
-    // stationarity w.r.t. x_N: -lam_{N-1} (x_N has no cost)
-    bool ok = true;
-    for (int k = N - 1; k >= 0; --k) {
-        double x[NX], u[NU], v[NU], r[NX], lam[NX], lam_prev[NX];
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-            x[i] = c.ld(c.W.X, k * NX + i);
-            r[i] = c.traj(k, i);
-            lam[i] = c.ld(c.W.LAM, k * NX + i);
-            lam_prev[i] = k ? c.ld(c.W.LAM, (k - 1) * NX + i) : 0.0;
-        }
-        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
-            u[j] = c.ld(c.W.U, k * NU + j);
-            v[j] = k ? c.ld(c.W.U, (k - 1) * NU + j) : c.uinit[j];
-        }
-        double F[NX], Fx[NX * NX], Fu[NX * NU], H[NH];
-        c.template step<2>(x, u, wq, r, lam, F, Fx, Fu, H);
-        double cres[NX], qe[NX];
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-            const double e = F[i] - r[i];
-            cres[i] = F[i] - xn[i];
-            qe[i] = wq[i] * e;
-            nrm.fval = fma(c.Q[i] * e, e, nrm.fval);
-            nrm.prim_inf = fmax(nrm.prim_inf, fabs(cres[i]));
-            nrm.theta += fabs(cres[i]);
-            nrm.lam_l1 += fabs(lam[i]);
-        }
-        // objective gradient pieces
-        double qx[NX], qu[NU], qv[NU], dRu[NU];
-        MMPC_UNROLL for (int j = 0; j < NX; ++j) {
-            double a = 0.0, l = 0.0;
-            MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-                a = fma(Fx[i * NX + j], qe[i], a);
-                l = fma(Fx[i * NX + j], lam[i], l);
-            }
-            qx[j] = a;
-            if (k) nrm.dual_inf = fmax(nrm.dual_inf, fabs(a + l - lam_prev[j]));
-        }
-        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
-            double a = 0.0, l = 0.0;
-            MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-                a = fma(Fu[i * NU + j], qe[i], a);
-                l = fma(Fu[i * NU + j], lam[i], l);
-            }
-            const double du = u[j] - v[j];
-            dRu[j] = 2.0 * c.R[j] * du;
-            qu[j] = a + dRu[j] + 2.0 * c.Rm[j] * u[j];
-            qv[j] = -dRu[j];
-            nrm.fval = fma(c.R[j] * du, du, nrm.fval);
-            nrm.fval = fma(c.Rm[j] * u[j], u[j], nrm.fval);
-            nrm.dual_inf = fmax(nrm.dual_inf, fabs(qu[j] + l - du_next[j]));
-            du_next[j] = dRu[j];
-        }
-        // full stage Hessian: H += Fz' (2Q) Fz ; uu diagonal += 2(R + Rm) (+ delta regularisation)
-        MMPC_UNROLL for (int a = 0; a < S; ++a) MMPC_UNROLL for (int d = a; d < S; ++d) {
-            double acc = H[tri(a, d, S)];
-            MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-                const double fa = a < NX ? Fx[i * NX + a] : Fu[i * NU + a - NX];
-                const double fd = d < NX ? Fx[i * NX + d] : Fu[i * NU + d - NX];
-                acc = fma(wq[i] * fa, fd, acc);
-            }
-            if (a == d) acc += delta + (a >= NX ? 2.0 * (c.R[a - NX] + c.Rm[a - NX]) : 0.0);
-            H[tri(a, d, S)] = acc;
-        }
-        // ---- Riccati update ----
-        double y[NX], yv[NU];
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-            double a = V.px[i];
-            MMPC_UNROLL for (int j = 0; j < NX; ++j) a = fma(V.Pxx[i * NX + j], cres[j], a);
-            y[i] = a;
-        }
-        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
-            double a = V.pv[j];
-            MMPC_UNROLL for (int i = 0; i < NX; ++i) a = fma(V.Pxv[i * NU + j], cres[i], a);
-            yv[j] = a;
-        }
-        double PA[NX * NX], PB[NX * NU];
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-            MMPC_UNROLL for (int j = 0; j < NX; ++j) {
-                double a = 0.0;
-                MMPC_UNROLL for (int l = 0; l < NX; ++l) a = fma(V.Pxx[i * NX + l], Fx[l * NX + j], a);
-                PA[i * NX + j] = a;
-            }
-            MMPC_UNROLL for (int j = 0; j < NU; ++j) {
-                double a = V.Pxv[i * NU + j];
-                MMPC_UNROLL for (int l = 0; l < NX; ++l) a = fma(V.Pxx[i * NX + l], Fu[l * NU + j], a);
-                PB[i * NU + j] = a;
-            }
-        }
-        double Gxx[NX * NX], Gxu[NX * NU], Guu[NU * NU], gx[NX], gu[NU];
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-            MMPC_UNROLL for (int j = i; j < NX; ++j) {
-                double a = H[tri(i, j, S)];
-                MMPC_UNROLL for (int l = 0; l < NX; ++l) a = fma(Fx[l * NX + i], PA[l * NX + j], a);
-                Gxx[i * NX + j] = a;
-                Gxx[j * NX + i] = a;
-            }
-            MMPC_UNROLL for (int j = 0; j < NU; ++j) {
-                double a = H[tri(i, NX + j, S)];
-                MMPC_UNROLL for (int l = 0; l < NX; ++l) a = fma(Fx[l * NX + i], PB[l * NU + j], a);
-                Gxu[i * NU + j] = a;
-            }
-            double a = qx[i];
-            MMPC_UNROLL for (int l = 0; l < NX; ++l) a = fma(Fx[l * NX + i], y[l], a);
-            gx[i] = a;
-        }
-        MMPC_UNROLL for (int i = 0; i < NU; ++i) {
-            MMPC_UNROLL for (int j = 0; j < NU; ++j) {
-                double a = (i <= j ? H[tri(NX + i, NX + j, S)] : H[tri(NX + j, NX + i, S)]) + V.Pvv[i * NU + j];
-                MMPC_UNROLL for (int l = 0; l < NX; ++l) {
-                    a = fma(Fu[l * NU + i], PB[l * NU + j], a);
-                    a = fma(V.Pxv[l * NU + i], Fu[l * NU + j], a);
-                }
-                Guu[i * NU + j] = a;
-            }
-            double a = qu[i] + yv[i];
-            MMPC_UNROLL for (int l = 0; l < NX; ++l) a = fma(Fu[l * NU + i], y[l], a);
-            gu[i] = a;
-        }
-        MMPC_UNROLL for (int i = 0; i < NU; ++i) MMPC_UNROLL for (int j = i + 1; j < NU; ++j) {  // symmetrise
-            const double a = 0.5 * (Guu[i * NU + j] + Guu[j * NU + i]);
-            Guu[i * NU + j] = Guu[j * NU + i] = a;
-        }
-        ok = chol<NU>(Guu) && ok;
-        // gains: Kx = -Guu^-1 Gxu', Kv = Guu^-1 (2R), k0 = -Guu^-1 gu
-        double Kx[NU * NX], Kv[NU * NU], k0[NU];
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-            double col[NU];
-            MMPC_UNROLL for (int j = 0; j < NU; ++j) col[j] = -Gxu[i * NU + j];
-            chol_solve<NU>(Guu, col);
-            MMPC_UNROLL for (int j = 0; j < NU; ++j) Kx[j * NX + i] = col[j];
-        }
-        MMPC_UNROLL for (int l = 0; l < NU; ++l) {
-            double col[NU];
-            MMPC_UNROLL for (int j = 0; j < NU; ++j) col[j] = (j == l) ? 2.0 * c.R[l] : 0.0;
-            chol_solve<NU>(Guu, col);
-            MMPC_UNROLL for (int j = 0; j < NU; ++j) Kv[j * NU + l] = col[j];
-        }
-        MMPC_UNROLL for (int j = 0; j < NU; ++j) k0[j] = -gu[j];
-        chol_solve<NU>(Guu, k0);
-        // store gains and the value function of stage k+1 (needed by the forward sweep for lam_k)
-        MMPC_UNROLL for (int i = 0; i < NU * NX; ++i) c.st(c.W.KX, k * NU * NX + i, Kx[i]);
-        MMPC_UNROLL for (int i = 0; i < NU * NU; ++i) c.st(c.W.KV, k * NU * NU + i, Kv[i]);
-        MMPC_UNROLL for (int i = 0; i < NU; ++i) c.st(c.W.K0, k * NU + i, k0[i]);
-        MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) c.st(c.W.PXX, k * NX * NX + i, V.Pxx[i]);
-        MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) c.st(c.W.PXV, k * NX * NU + i, V.Pxv[i]);
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) c.st(c.W.PX, k * NX + i, V.px[i]);
-        // new value function
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-            MMPC_UNROLL for (int j = i; j < NX; ++j) {
-                double a = Gxx[i * NX + j];
-                MMPC_UNROLL for (int l = 0; l < NU; ++l) a = fma(Gxu[i * NU + l], Kx[l * NX + j], a);
-                V.Pxx[i * NX + j] = a;
-                V.Pxx[j * NX + i] = a;
-            }
-            MMPC_UNROLL for (int j = 0; j < NU; ++j) {
-                double a = 0.0;
-                MMPC_UNROLL for (int l = 0; l < NU; ++l) a = fma(Gxu[i * NU + l], Kv[l * NU + j], a);
-                V.Pxv[i * NU + j] = a;
-            }
-            double a = gx[i];
-            MMPC_UNROLL for (int l = 0; l < NU; ++l) a = fma(Gxu[i * NU + l], k0[l], a);
-            V.px[i] = a;
-        }
-        MMPC_UNROLL for (int i = 0; i < NU; ++i) {
-            MMPC_UNROLL for (int j = 0; j < NU; ++j) V.Pvv[i * NU + j] = (i == j ? 2.0 * c.R[i] : 0.0) - 2.0 * c.R[i] * Kv[i * NU + j];
-            V.pv[i] = qv[i] - 2.0 * c.R[i] * k0[i];
-        }
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) xn[i] = x[i];
-        if (k == N - 1) {  // stationarity w.r.t. x_N is -lam_{N-1}
-            MMPC_UNROLL for (int i = 0; i < NX; ++i) nrm.dual_inf = fmax(nrm.dual_inf, fabs(lam[i]));
-        }
-    }
-    return ok;
-}
-
-// forward sweep: step, new multipliers, directional derivative of f, and merit pieces of the full step.
-template <class M>
-__device__ void forward_sweep(const SolveCtx<M>& c, double& gradf_d, double& lam_inf, double& f1, double& theta1, bool& finite) {
-    constexpr int NX = M::NX, NU = M::NU;
-    const int N = c.P.N;
-    double dx[NX], dv[NU], wq[NX];
-    MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-        dx[i] = 0.0;
-        wq[i] = 2.0 * c.Q[i];
-    }
-    MMPC_UNROLL for (int j = 0; j < NU; ++j) dv[j] = 0.0;
-    gradf_d = 0.0; lam_inf = 0.0; f1 = 0.0; theta1 = 0.0; finite = true;
-    double x[NX];
-    MMPC_UNROLL for (int i = 0; i < NX; ++i) x[i] = c.ld(c.W.X, i);
-    for (int k = 0; k < N; ++k) {
-        double u[NU], v[NU], r[NX], xn[NX];
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-            r[i] = c.traj(k, i);
-            xn[i] = c.ld(c.W.X, (k + 1) * NX + i);
-        }
-        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
-            u[j] = c.ld(c.W.U, k * NU + j);
-            v[j] = k ? c.ld(c.W.U, (k - 1) * NU + j) : c.uinit[j];
-        }
-        double F[NX], Fx[NX * NX], Fu[NX * NU];
-        c.template step<1>(x, u, nullptr, nullptr, nullptr, F, Fx, Fu, nullptr);
-        double du[NU];
-        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
-            double a = c.ld(c.W.K0, k * NU + j);
-            MMPC_UNROLL for (int i = 0; i < NX; ++i) a = fma(c.ld(c.W.KX, (k * NU + j) * NX + i), dx[i], a);
-            MMPC_UNROLL for (int l = 0; l < NU; ++l) a = fma(c.ld(c.W.KV, (k * NU + j) * NU + l), dv[l], a);
-            du[j] = a;
-            c.st(c.W.DU, k * NU + j, a);
-            finite = finite && isfinite(a);
-        }
-        double dxn[NX];
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-            double a = F[i] - xn[i];
-            MMPC_UNROLL for (int j = 0; j < NX; ++j) a = fma(Fx[i * NX + j], dx[j], a);
-            MMPC_UNROLL for (int j = 0; j < NU; ++j) a = fma(Fu[i * NU + j], du[j], a);
-            dxn[i] = a;
-            c.st(c.W.DX, (k + 1) * NX + i, a);
-            // directional derivative of e'Qe: 2 Q e . (Fx dx + Fu du) = 2 Q e . (dxn - c)
-            gradf_d = fma(wq[i] * (F[i] - r[i]), a - (F[i] - xn[i]), gradf_d);
-        }
-        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
-            gradf_d = fma(2.0 * c.R[j] * (u[j] - v[j]), du[j] - dv[j], gradf_d);
-            gradf_d = fma(2.0 * c.Rm[j] * u[j], du[j], gradf_d);
-        }
-        // multiplier of g_k from the value function of stage k+1
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-            double a = c.ld(c.W.PX, k * NX + i);
-            MMPC_UNROLL for (int j = 0; j < NX; ++j) a = fma(c.ld(c.W.PXX, (k * NX + i) * NX + j), dxn[j], a);
-            MMPC_UNROLL for (int j = 0; j < NU; ++j) a = fma(c.ld(c.W.PXV, (k * NX + i) * NU + j), du[j], a);
-            c.st(c.W.LAMN, k * NX + i, a);
-            lam_inf = fmax(lam_inf, fabs(a));
-        }
-        // fused trial evaluation of the full step at node k
-        {
-            double xt[NX], ut[NU], Ft[NX];
-            MMPC_UNROLL for (int i = 0; i < NX; ++i) xt[i] = x[i] + dx[i];
-            MMPC_UNROLL for (int j = 0; j < NU; ++j) ut[j] = u[j] + du[j];
-            c.template step<0>(xt, ut, nullptr, nullptr, nullptr, Ft, nullptr, nullptr, nullptr);
-            MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-                const double e = Ft[i] - r[i];
-                f1 = fma(c.Q[i] * e, e, f1);
-                theta1 += fabs(Ft[i] - (xn[i] + dxn[i]));
-            }
-            MMPC_UNROLL for (int j = 0; j < NU; ++j) {
-                const double d = ut[j] - (v[j] + dv[j]);
-                f1 = fma(c.R[j] * d, d, f1);
-                f1 = fma(c.Rm[j] * ut[j], ut[j], f1);
-            }
-        }
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-            x[i] = xn[i];
-            dx[i] = dxn[i];
-        }
-        MMPC_UNROLL for (int j = 0; j < NU; ++j) dv[j] = du[j];
-    }
-}
-
-// merit pieces at z + alpha dz
-template <class M>
-__device__ void trial_eval(const SolveCtx<M>& c, double alpha, double& f1, double& theta1) {
-    constexpr int NX = M::NX, NU = M::NU;
-    const int N = c.P.N;
-    f1 = 0.0; theta1 = 0.0;
-    double x[NX], v[NU];
-    MMPC_UNROLL for (int i = 0; i < NX; ++i) x[i] = c.ld(c.W.X, i);
-    MMPC_UNROLL for (int j = 0; j < NU; ++j) v[j] = c.uinit[j];
-    for (int k = 0; k < N; ++k) {
-        double u[NU], xn[NX], F[NX];
-        MMPC_UNROLL for (int j = 0; j < NU; ++j) u[j] = fma(alpha, c.ld(c.W.DU, k * NU + j), c.ld(c.W.U, k * NU + j));
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) xn[i] = fma(alpha, c.ld(c.W.DX, (k + 1) * NX + i), c.ld(c.W.X, (k + 1) * NX + i));
-        c.template step<0>(x, u, nullptr, nullptr, nullptr, F, nullptr, nullptr, nullptr);
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-            const double e = F[i] - c.traj(k, i);
-            f1 = fma(c.Q[i] * e, e, f1);
-            theta1 += fabs(F[i] - xn[i]);
-            x[i] = xn[i];
-        }
-        MMPC_UNROLL for (int j = 0; j < NU; ++j) {
-            const double d = u[j] - v[j];
-            f1 = fma(c.R[j] * d, d, f1);
-            f1 = fma(c.Rm[j] * u[j], u[j], f1);
-            v[j] = u[j];
-        }
-    }
-}
-
-template <class M>
-__global__ void __launch_bounds__(32) solve_kernel_t1(mmpc_problem P, mmpc_workspace W, mmpc_solve_io io) {
-    constexpr int NX = M::NX, NU = M::NU, S = NX + NU;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= W.B) return;
-    const int N = P.N;
-    SolveCtx<M> c(P, W, io, b);
-    MMPC_UNROLL for (int i = 0; i < NX; ++i) c.Q[i] = c.ld(W.Qw, i);
-    MMPC_UNROLL for (int j = 0; j < NU; ++j) {
-        c.R[j] = c.ld(W.Rw, j);
-        c.Rm[j] = c.ld(W.Rmw, j);
-        c.uinit[j] = io.control[(size_t)b * NU + j];
-    }
-    // ---- start point: warm = previous solution of this slot (ModelControl.cpp:161), else zeros (:28-50) ----
-    const bool warm = io.warm_start && W.have_warm;
-    if (!warm) {
-        for (int r = NX; r < (N + 1) * NX; ++r) c.st(W.X, r, 0.0);
-        for (int r = 0; r < N * NU; ++r) c.st(W.U, r, 0.0);
-    }
-    if (!(warm && io.warm_start_duals))
-        for (int r = 0; r < N * NX; ++r) c.st(W.LAM, r, 0.0);
-    double x0[NX];
-    MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-        x0[i] = io.state[(size_t)b * NX + i];
-        c.st(W.X, i, x0[i]);  // x_0 pinned (ModelControl.cpp:144-145)
-    }
-    if (P.is_linear) {  // A, B, xdot at (state, control) (ModelControl.cpp:125-135), kept row-major
-        double xd[NX], A[NX * NX], Bm[NX * NU];
-        M::fAB(x0, c.uinit, xd, A, Bm);
-        MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) c.st(W.LIN, i, A[i]);
-        MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) c.st(W.LIN, NX * NX + i, Bm[i]);
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) c.st(W.LIN, NX * NX + NX * NU + i, xd[i]);
-    }
-    double nu_merit = 1.0, delta_last = 0.0, err = INFINITY, fval = 0.0;
-    int it = 0, status = MMPC_SOLVE_MAX_ITER, ls_total = 0, reg_total = 0;
-    const int nfree = N * S, ncon = N * NX;  // free variables: u_0, (x_k,u_k) k=1..N-1, x_N
-    for (it = 0;; ++it) {
-        SweepNorms nrm;
-        double delta = 0.0;
-        bool ok = backward_sweep<M>(c, delta, nrm);
-        // IPOPT scaled optimality error (Waechter & Biegler 2006 eq. 5) [upstream]: s_max = 100
-        const double sd = fmax(100.0, nrm.lam_l1 / (double)(nfree + ncon)) / 100.0;
-        err = fmax(nrm.dual_inf / sd, nrm.prim_inf);
-        fval = nrm.fval;
-        if (!isfinite(err)) { status = MMPC_SOLVE_NUMERICAL; break; }
-        if (err <= io.tol) { status = MMPC_SOLVE_CONVERGED; break; }
-        if (it >= io.max_iter) { status = MMPC_SOLVE_MAX_ITER; break; }
-        // inertia correction: retry the sweep with delta on the diagonal until every G_uu is PD
-        int tries = 0;
-        while (!ok && tries < 24) {
-            delta = (delta == 0.0) ? (delta_last > 0.0 ? fmax(1e-20, delta_last / 3.0) : 1e-4) : delta * 8.0;
-            SweepNorms dummy;
-            ok = backward_sweep<M>(c, delta, dummy);
-            ++tries; ++reg_total;
-        }
-        if (!ok) { status = MMPC_SOLVE_NUMERICAL; break; }
-        if (delta > 0.0) delta_last = delta;
-        double gd, lam_inf, f1, th1;
-        bool finite;
-        forward_sweep<M>(c, gd, lam_inf, f1, th1, finite);
-        if (!finite) { status = MMPC_SOLVE_NUMERICAL; break; }
-        nu_merit = fmax(nu_merit, 1.1 * lam_inf + 1e-8);
-        const double m0 = nrm.fval + nu_merit * nrm.theta;
-        const double D = gd - nu_merit * nrm.theta;
-        double alpha = 1.0;
-        for (int ls = 0; ls < 40; ++ls) {
-            if (f1 + nu_merit * th1 <= m0 + 1e-4 * alpha * D + 1e-12 * fabs(m0)) break;
-            alpha *= 0.5;
-            ++ls_total;
-            trial_eval<M>(c, alpha, f1, th1);
-        }
-        for (int r = NX; r < (N + 1) * NX; ++r) c.st(W.X, r, fma(alpha, c.ld(W.DX, r), c.ld(W.X, r)));
-        for (int r = 0; r < N * NU; ++r) c.st(W.U, r, fma(alpha, c.ld(W.DU, r), c.ld(W.U, r)));
-        for (int r = 0; r < N * NX; ++r) {
-            const double l = c.ld(W.LAM, r);
-            c.st(W.LAM, r, fma(alpha, c.ld(W.LAMN, r) - l, l));
-        }
-    }
-    // ---- outputs in the reference's V layout (ModelGenerator.cpp:76-112; unpacked ModelControl.cpp:174-190) ----
-    const int NV = NX * (N + 1) + NU * N;
-    double* Vb = io.V_out + (size_t)b * NV;
-    for (int k = 0; k <= N; ++k) {
-        MMPC_UNROLL for (int i = 0; i < NX; ++i) Vb[k * S + i] = c.ld(W.X, k * NX + i);
-        if (k < N) MMPC_UNROLL for (int j = 0; j < NU; ++j) Vb[k * S + NX + j] = c.ld(W.U, k * NU + j);
-    }
-    if (io.lam_out)
-        for (int r = 0; r < N * NX; ++r) io.lam_out[(size_t)b * N * NX + r] = c.ld(W.LAM, r);
-    if (io.stats) {
-        mmpc_stats s;
-        s.objective = fval; s.kkt_error = err; s.mu = 0.0; s.iterations = it; s.status = status;
-        s.ls_steps = ls_total; s.reg_steps = reg_total;
-        io.stats[b] = s;
-    }
-}
-
 }  // namespace mmpc
+#include "mmpc_solve_t1.cuh"
 #include "mmpc_solve_t2.cuh"
 namespace mmpc {
 
@@ -779,10 +341,15 @@ struct Launch {
         return cudaGetLastError();
     }
     static cudaError_t solve(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st, int* launches) {
-        if (P.integrator != MMPC_EULER || P.bounded) return cudaErrorNotSupported;
+        if (P.integrator != MMPC_EULER) return cudaErrorNotSupported;
+        if (W.variant == 2) {
+            if (P.bounded) return cudaErrorNotSupported;  // bounds are implemented by T1 (the ABI layer switches variants)
+            if (launches) ++*launches;
+            return LaunchT2<M>::run(P, W, io, st);
+        }
         if (launches) ++*launches;
-        if (W.variant == 2) return LaunchT2<M>::run(P, W, io, st);
-        solve_kernel_t1<M><<<(W.B + 31) / 32, 32, 0, st>>>(P, W, io);
+        if (P.bounded) solve_kernel_t1<M, true><<<(W.B + 31) / 32, 32, 0, st>>>(P, W, io);
+        else solve_kernel_t1<M, false><<<(W.B + 31) / 32, 32, 0, st>>>(P, W, io);
         return cudaGetLastError();
     }
 };

@@ -11,6 +11,7 @@ pytestmark = pytest.mark.gpu
 EVAL_RTOL = 1e-12   # north_star: "within 1e-12 relative error in fp64"
 U_ATOL = 1e-6       # north_star: "within 1e-6 on controls"
 OBJ_RTOL = 1e-8     # north_star: "1e-8 relative on the objective"
+NB = 10e30      # the reference's "no bound" sentinel (ModelParameters.cpp:21-24)
 
 
 def rel(a, b):
@@ -261,3 +262,58 @@ def test_solve_per_instance_weights_and_errors(api):
         api.Solver(m, 0)
     with pytest.raises(api.MmpcError):
         api.Model("no_such_model", N=5, nx=3, nu=1)
+
+
+def test_bounded_solve_vs_golden(api, golden):
+    """Finite control limits (ModelControl::update_control_limits, ModelControl.cpp:205-209): interior-point path."""
+    gs = golden["solves"]
+    n = 0
+    for case in gs["cases"]:
+        if not case["u_bound"]:
+            continue
+        n += 1
+        N, ub = case["N"], case["u_bound"]
+        P = nlp.Problem(N=N)
+        pv = P.split_p(np.array(case["p"]))
+        m = api.Model("double_pendulum", N=N)
+        s = api.Solver(m, 1, tol=1e-9)
+        s.set_weights(pv["Q"], pv["R"], pv["Rm"])
+        s.set_bounds(u_min=[-ub, -ub], u_max=[ub, ub])
+        V, lam, st = s.solve(np.array(case["x0"])[None], pv["u_init"][None].copy(), pv["r"][None].copy())
+        assert st["status"][0] == 0, st
+        Vg = np.array(case["V"])
+        U = V[0, :N * 6].reshape(N, 6)[:, 4:]
+        assert np.abs(U).max() <= ub and np.abs(U).max() > ub - 1e-6  # the limit is active and respected
+        assert np.abs(V[0] - Vg).max() < U_ATOL
+        assert abs(st["objective"][0] - case["f"]) <= OBJ_RTOL * abs(case["f"])
+    assert n == 2
+
+
+@pytest.mark.parametrize("N,B,ub,xb", [(25, 16, 2.5, None), (50, 40, 1.5, None), (25, 8, 4.0, 0.9)])
+def test_bounded_solve_vs_oracle(api, coracle, N, B, ub, xb):
+    P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B, seed_offset=300)
+    x_min = x_max = None
+    if xb is not None:  # also a state bound on the first joint velocity-like state
+        x_min, x_max = [-NB, -NB, -NB, -NB], [xb, NB, NB, NB]
+    m = api.Model("double_pendulum", N=N, u_min=[-ub, -ub], u_max=[ub, ub], x_min=x_min, x_max=x_max)
+    s = api.Solver(m, B, tol=1e-10)  # same barrier end point (mu = tol/10) on both sides
+    s.set_weights(Q, R, Rm)
+    V, lam, st = s.solve(x0, up, traj)
+    lb, ubv = nlp.bounds_vectors(P, x0[0], x_min=x_min, x_max=x_max, u_min=[-ub] * 2, u_max=[ub] * 2)
+    Vo, _, sto, bad = coracle.solve_batch("double_pendulum", N, P.h, False, x0, p, lb=lb, ub=ubv, tol=1e-10)
+    good = (sto["status"] == 0)
+    assert good.sum() >= B - 1 and (st["status"][good] == 0).all(), (st["status"], sto["status"])
+    assert np.abs(V[good] - Vo[good]).max() < U_ATOL
+    assert (np.abs(st["objective"] - sto["f"])[good] <= OBJ_RTOL * np.abs(sto["f"][good])).all()
+    U = V[:, :N * 6].reshape(B, N, 6)[:, :, 4:]
+    assert np.abs(U).max() <= ub
+    if xb is not None:
+        assert V[:, 6::6][:, :N].max() <= xb + 1e-12
+    # unbounded handle switched to bounds later (update_control_limits) gives the same answer
+    m2 = api.Model("double_pendulum", N=N)
+    s2 = api.Solver(m2, B, tol=1e-10)
+    s2.set_weights(Q, R, Rm)
+    s2.solve(x0, up, traj)
+    s2.set_bounds(x_min=x_min, x_max=x_max, u_min=[-ub, -ub], u_max=[ub, ub])
+    V2, _, st2 = s2.solve(x0, up, traj)
+    assert np.abs(V2[good] - V[good]).max() < 1e-7
