@@ -158,11 +158,17 @@ inline std::string quote(const std::string& s) {
     }
     return o + "\"";
 }
-// shortest round-trip representation, integers without exponent where nlohmann would print them so
+// shortest representation that parses back to the same double (1e+31 rather than 9.9999999999999996e+30)
 inline std::string number(double d) {
     char buf[64];
-    if (d == std::floor(d) && std::fabs(d) < 1e15) std::snprintf(buf, sizeof(buf), "%.1f", d);
-    else std::snprintf(buf, sizeof(buf), "%.17g", d);
+    if (d == std::floor(d) && std::fabs(d) < 1e15) {
+        std::snprintf(buf, sizeof(buf), "%.1f", d);
+        return buf;
+    }
+    for (int prec = 1; prec <= 17; ++prec) {
+        std::snprintf(buf, sizeof(buf), "%.*g", prec, d);
+        if (std::strtod(buf, nullptr) == d) break;
+    }
     return buf;
 }
 
