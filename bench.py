@@ -239,13 +239,12 @@ def run_gpu(args):
     # ---- final gather of plans + statistics to rank 0 (the only NVLink traffic) -----------
     gather_ms = None
     if world > 1:
-        bufs = [torch.empty_like(d_V) for _ in range(world)] if rank == 0 else None
-        sbufs = [torch.empty_like(d_st) for _ in range(world)] if rank == 0 else None
+        from mahi_mpc_b200 import shard
+        shard.gather_to_root([d_V, d_st])  # warm-up (NCCL communicator setup)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        dist.gather(d_V, bufs, dst=0)
-        dist.gather(d_st, sbufs, dst=0)
+        gathered = shard.gather_to_root([d_V, d_st])
         g1.record()
         barrier()
         t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
