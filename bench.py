@@ -39,6 +39,9 @@ N_NODES, BATCH, NX, NU, H_STEP = 50, 4096, 4, 2, 0.002
 WORKLOAD = "BASELINE configs[1]: double pendulum (ex_model_generate), N=50, batch 4096 per GPU, cold start, tol 1e-5"
 
 
+print_json = lambda obj: print(json.dumps(obj))
+
+
 def workload(batch, offset=0):
     from mahi_mpc_b200 import workload as w  # synthetic-input generator; identical to the oracle's copy
     x0, up, traj = w.synthetic_batch(NX, NU, N_NODES, H_STEP, batch, offset=offset)
@@ -145,7 +148,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print_json(line)
     return 0
 
 
@@ -295,7 +298,7 @@ def run_gpu(args):
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "fp64_roofline": fp64,
             "cpu_baseline": cpu, "node_eval": extras, "latency": lat, "gather_ms": gather_ms,
         }
-        print(json.dumps(line))
+        print_json(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -354,9 +357,22 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="solve kernel variant (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_gpu(args)
+    # Libraries (NCCL prints its version banner) write to fd 1; the contract wants exactly ONE JSON line on stdout.
+    # Route fd 1 to stderr for the duration of the run and emit the JSON line on the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    global print_json
+    print_json = lambda obj: lines.append(json.dumps(obj))
+    try:
+        rc = run_reference(args) if args.impl == "reference" else run_gpu(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+    for ln in lines:
+        os.write(1, (ln + "\n").encode())
+    return rc
 
 
 if __name__ == "__main__":
