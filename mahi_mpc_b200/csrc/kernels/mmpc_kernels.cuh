@@ -298,6 +298,7 @@ __device__ __forceinline__ void chol_solve(const double* L, double* b) {
 }  // namespace mmpc
 #include "mmpc_solve_t1.cuh"
 #include "mmpc_solve_t2.cuh"
+#include "mmpc_solve_t3.cuh"
 namespace mmpc {
 
 // ---------------------------------------------------------------------------------------------
@@ -342,10 +343,10 @@ struct Launch {
     }
     static cudaError_t solve(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st, int* launches) {
         if (P.integrator != MMPC_EULER) return cudaErrorNotSupported;
-        if (W.variant == 2) {
+        if (W.variant == 2 || W.variant == 3) {
             if (P.bounded) return cudaErrorNotSupported;  // bounds are implemented by T1 (the ABI layer switches variants)
             if (launches) ++*launches;
-            return LaunchT2<M>::run(P, W, io, st);
+            return W.variant == 2 ? LaunchT2<M>::run(P, W, io, st) : LaunchT3<M>::run(P, W, io, st);
         }
         if (launches) ++*launches;
         if (P.bounded) solve_kernel_t1<M, true><<<(W.B + 31) / 32, 32, 0, st>>>(P, W, io);

@@ -157,7 +157,7 @@ def test_solve_vs_golden(api, golden):
         assert rel(lam[0], case["lam_g"]) < 1e-6
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("N,B", [(1, 3), (10, 7), (25, 33), (50, 64), (100, 8), (200, 4)])
 def test_solve_vs_oracle(api, coracle, N, B, variant):
     P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B)
