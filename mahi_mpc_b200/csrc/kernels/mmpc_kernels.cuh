@@ -341,32 +341,62 @@ struct Launch {
         if (launches) ++*launches;
         return cudaGetLastError();
     }
-    static cudaError_t solve(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st, int* launches) {
-        if (P.integrator != MMPC_EULER) return cudaErrorNotSupported;
-        if (W.variant == 2 || W.variant == 3) {
-            if (P.bounded) return cudaErrorNotSupported;  // bounds are implemented by T1 (the ABI layer switches variants)
-            if (launches) ++*launches;
-            return W.variant == 2 ? LaunchT2<M>::run(P, W, io, st) : LaunchT3<M>::run(P, W, io, st);
-        }
-        if (launches) ++*launches;
+    // per-variant launchers; each may live in its own translation unit (MMPC_DEFINE_SOLVE_T*)
+    static cudaError_t solve_t1(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         if (P.bounded) solve_kernel_t1<M, true><<<(W.B + 31) / 32, 32, 0, st>>>(P, W, io);
         else solve_kernel_t1<M, false><<<(W.B + 31) / 32, 32, 0, st>>>(P, W, io);
         return cudaGetLastError();
+    }
+    static cudaError_t solve_t2(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
+        return LaunchT2<M>::run(P, W, io, st);
+    }
+    static cudaError_t solve_t3(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
+        return LaunchT3<M>::run(P, W, io, st);
     }
 };
 
 }  // namespace mmpc
 
-// Defines `mmpc_vtable_<MODEL>()` for the generated functor `mmpc_model_<MODEL>`.
-#define MMPC_DEFINE_MODEL(MODEL)                                                                                         \
-    extern "C" const mmpc_model_vtable* mmpc_vtable_##MODEL(void) {                                                       \
-        using M = mmpc_model_##MODEL;                                                                                     \
-        static const mmpc_model_vtable vt = {MMPC_VTABLE_VERSION, M::MODEL_NAME, M::NX, M::NU,                            \
-                                             {M::OPS_F, M::TRANS_F, M::OPS_FAB, M::TRANS_FAB, M::OPS_FABH, M::TRANS_FABH}, \
-                                             &mmpc::Launch<M>::eval_nodes, &mmpc::Launch<M>::linearise,                   \
-                                             &mmpc::Launch<M>::nlp_eval, &mmpc::Launch<M>::solve};                        \
-        return &vt;                                                                                                       \
+// ---- translation-unit macros --------------------------------------------------------------------------------
+// The three solve variants of a model can be compiled in separate units (parallel builds of large generated models):
+#define MMPC_DEFINE_SOLVE_T1(MODEL)                                                                                    \
+    extern "C" cudaError_t mmpc_solve_t1_##MODEL(const mmpc_problem* P, const mmpc_workspace* W, const mmpc_solve_io* io, cudaStream_t st) { \
+        return mmpc::Launch<mmpc_model_##MODEL>::solve_t1(*P, *W, *io, st);                                             \
     }
+#define MMPC_DEFINE_SOLVE_T2(MODEL)                                                                                    \
+    extern "C" cudaError_t mmpc_solve_t2_##MODEL(const mmpc_problem* P, const mmpc_workspace* W, const mmpc_solve_io* io, cudaStream_t st) { \
+        return mmpc::Launch<mmpc_model_##MODEL>::solve_t2(*P, *W, *io, st);                                             \
+    }
+#define MMPC_DEFINE_SOLVE_T3(MODEL)                                                                                    \
+    extern "C" cudaError_t mmpc_solve_t3_##MODEL(const mmpc_problem* P, const mmpc_workspace* W, const mmpc_solve_io* io, cudaStream_t st) { \
+        return mmpc::Launch<mmpc_model_##MODEL>::solve_t3(*P, *W, *io, st);                                             \
+    }
+// ... and this one defines the evaluators, the solve dispatcher and `mmpc_vtable_<MODEL>()`:
+#define MMPC_DEFINE_MODEL_CORE(MODEL)                                                                                   \
+    extern "C" cudaError_t mmpc_solve_t1_##MODEL(const mmpc_problem*, const mmpc_workspace*, const mmpc_solve_io*, cudaStream_t); \
+    extern "C" cudaError_t mmpc_solve_t2_##MODEL(const mmpc_problem*, const mmpc_workspace*, const mmpc_solve_io*, cudaStream_t); \
+    extern "C" cudaError_t mmpc_solve_t3_##MODEL(const mmpc_problem*, const mmpc_workspace*, const mmpc_solve_io*, cudaStream_t); \
+    static cudaError_t mmpc_solve_dispatch_##MODEL(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io,  \
+                                                   cudaStream_t st, int* launches) {                                    \
+        if (P.integrator != MMPC_EULER) return cudaErrorNotSupported;                                                   \
+        /* bounds are implemented by T1 only (the ABI layer switches variants) */                                        \
+        if ((W.variant == 2 || W.variant == 3) && P.bounded) return cudaErrorNotSupported;                              \
+        if (launches) ++*launches;                                                                                      \
+        if (W.variant == 2) return mmpc_solve_t2_##MODEL(&P, &W, &io, st);                                              \
+        if (W.variant == 3) return mmpc_solve_t3_##MODEL(&P, &W, &io, st);                                              \
+        return mmpc_solve_t1_##MODEL(&P, &W, &io, st);                                                                  \
+    }                                                                                                                   \
+    extern "C" const mmpc_model_vtable* mmpc_vtable_##MODEL(void) {                                                      \
+        using M = mmpc_model_##MODEL;                                                                                    \
+        static const mmpc_model_vtable vt = {MMPC_VTABLE_VERSION, M::MODEL_NAME, M::NX, M::NU,                           \
+                                             {M::OPS_F, M::TRANS_F, M::OPS_FAB, M::TRANS_FAB, M::OPS_FABH, M::TRANS_FABH}, \
+                                             &mmpc::Launch<M>::eval_nodes, &mmpc::Launch<M>::linearise,                  \
+                                             &mmpc::Launch<M>::nlp_eval, &mmpc_solve_dispatch_##MODEL};                  \
+        return &vt;                                                                                                      \
+    }
+// everything in one unit (what ModelGenerator::generate_c_code emits for a user model)
+#define MMPC_DEFINE_MODEL(MODEL) \
+    MMPC_DEFINE_SOLVE_T1(MODEL) MMPC_DEFINE_SOLVE_T2(MODEL) MMPC_DEFINE_SOLVE_T3(MODEL) MMPC_DEFINE_MODEL_CORE(MODEL)
 // Additionally exports the generic entry point a stand-alone generated model library is dlopen'ed by
 // (the role `nlpsol("nlpsol","ipopt",dll,...)` plays at ModelControl.cpp:61-62).
 #define MMPC_EXPORT_MODEL_ENTRY(MODEL) \

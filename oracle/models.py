@@ -152,9 +152,41 @@ def derive(name: str):
     return dict(model=mdl, A=A, B=B, w=list(w), Hc=Hc)
 
 
+def _numeric_arm4():
+    """arm4: sympy is far too slow for its second derivatives (expression swell), so the numpy oracle borrows the C
+    oracle's forward-mode AD restatement (oracle/arm4_jets.c) through oracle/coracle.py."""
+    from . import coracle
+    co = coracle.COracle("O3")
+
+    def _call(x, u, w=None):
+        x = np.atleast_2d(np.asarray(x, float).T); u = np.atleast_2d(np.asarray(u, float).T)
+        wt = None if w is None else np.atleast_2d(np.asarray(w, float).T)
+        return co.node_eval("arm4", 1.0, x, u, np.zeros_like(x), wt), x
+
+    def f_np(x, u):
+        (g, _, _, _), xt = _call(x, u)
+        return (g - xt).T
+
+    def A_np(x, u):
+        (_, Fx, _, _), _ = _call(x, u)
+        return np.moveaxis(Fx - np.eye(8), 0, 2)
+
+    def B_np(x, u):
+        (_, _, Fu, _), _ = _call(x, u)
+        return np.moveaxis(Fu, 0, 2)
+
+    def Hc_np(x, u, w):
+        (_, _, _, H), _ = _call(x, u, w)
+        return np.moveaxis(H, 0, 2)
+
+    return dict(nx=8, nu=4, f=f_np, A=A_np, B=B_np, Hc=Hc_np)
+
+
 @functools.lru_cache(maxsize=None)
 def numeric(name: str):
     """numpy-callable f, A, B, Hc (vectorised over a trailing batch axis)."""
+    if name == "arm4":
+        return _numeric_arm4()
     d = derive(name)
     mdl = d["model"]
     args = mdl.z

@@ -24,9 +24,7 @@
 #endif
 
 #include "gen/double_pendulum_gen.c"
-#ifdef ORACLE_HAVE_ARM4
-#include "gen/arm4_gen.c"
-#endif
+#include "arm4_jets.c" /* builder-defined 4-DOF arm (BASELINE config 3): second-order forward-mode AD, no generated code */
 
 #define MAXNX 8
 #define MAXNU 4
@@ -43,9 +41,7 @@ typedef struct {
 
 static const omodel_t g_models[] = {
     {"double_pendulum", 4, 2, double_pendulum_f, double_pendulum_fAB, double_pendulum_fABH},
-#ifdef ORACLE_HAVE_ARM4
     {"arm4", 8, 4, arm4_f, arm4_fAB, arm4_fABH},
-#endif
 };
 
 int oracle_model_index(const char* name) {

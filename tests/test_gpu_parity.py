@@ -317,3 +317,60 @@ def test_bounded_solve_vs_oracle(api, coracle, N, B, ub, xb):
     s2.set_bounds(x_min=x_min, x_max=x_max, u_min=[-ub, -ub], u_max=[ub, ub])
     V2, _, st2 = s2.solve(x0, up, traj)
     assert np.abs(V2[good] - V[good]).max() < 1e-7
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE config 3: 4-DOF arm (builder-defined).  Oracle = oracle/arm4_jets.c (forward-mode AD over the
+# closed-form mass matrix), product = symbolic engine + generated CUDA: two independent derivations.
+# ---------------------------------------------------------------------------------------------------------------
+def test_arm4_eval_nodes_vs_oracle(api, coracle):
+    rng = np.random.default_rng(44)
+    n = 3000
+    x = np.c_[rng.uniform(-1.5, 1.5, (n, 4)), rng.uniform(-2, 2, (n, 4))]
+    u = rng.uniform(-3, 3, (n, 4)); xn = rng.uniform(-1, 1, (n, 8)); w = rng.uniform(-1, 1, (n, 8))
+    m = api.Model("arm4", N=10)
+    assert (m.nx, m.nu, m.NV, m.np) == (8, 4, 128, 10 * 8 + 8 + 12)
+    g, Fx, Fu, H = m.eval_nodes(x.T.copy(), u.T.copy(), xn.T.copy(), w.T.copy())
+    go, Fxo, Fuo, Ho = coracle.node_eval("arm4", m.h, x, u, xn, w)
+    iu = np.triu_indices(12)
+    assert rel(g.T, go) < EVAL_RTOL and rel(Fx.T.reshape(n, 8, 8), Fxo) < EVAL_RTOL and rel(Fu.T.reshape(n, 8, 4), Fuo) < EVAL_RTOL
+    assert rel(H.T, Ho[:, iu[0], iu[1]]) < 1e-11  # sums of ~1e4 terms: one more digit of slack than the 1e-12 of the pendulum
+
+
+def _arm_inputs(N, B):
+    from mahi_mpc_b200 import workload
+    P = nlp.Problem(model="arm4", N=N)
+    Q, R, Rm = workload.default_weights(8, 4)
+    x0, up, traj = workload.synthetic_batch(8, 4, N, P.h, B)
+    traj *= 0.5
+    p = np.stack([P.pack_p(traj[b], Q, R, Rm, up[b]) for b in range(B)])
+    return P, (Q, R, Rm), x0, up, traj, p
+
+
+def test_arm4_nlp_eval_vs_oracle(api, coracle):
+    N, B = 12, 3
+    P, (Q, R, Rm), x0, up, traj, p = _arm_inputs(N, B)
+    rng = np.random.default_rng(45)
+    V = rng.uniform(-0.5, 0.5, (B, P.NV)); lam = rng.uniform(-1, 1, (B, P.M))
+    m = api.Model("arm4", N=N)
+    out = m.nlp_eval(V, p, lam, lam_f=1.0)
+    for b in range(B):
+        o = coracle.nlp_eval("arm4", N, P.h, False, V[b], p[b], lam[b], 1.0)
+        assert abs(out["f"][b] - o["f"]) <= EVAL_RTOL * abs(o["f"])
+        for k in ("g", "grad_f", "Fx", "Fu"):
+            assert rel(out[k][b], o[k]) < EVAL_RTOL, k
+        assert rel(out["Hzz"][b], o["Hzz"]) < 1e-11
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_arm4_solve_vs_oracle(api, coracle, variant):
+    N, B = 20, 9
+    P, (Q, R, Rm), x0, up, traj, p = _arm_inputs(N, B)
+    m = api.Model("arm4", N=N)
+    s = api.Solver(m, B, tol=1e-10, kernel_variant=variant)
+    s.set_weights(Q, R, Rm)
+    V, lam, st = s.solve(x0, up, traj)
+    Vo, lamo, sto, bad = coracle.solve_batch("arm4", N, P.h, False, x0, p, tol=1e-10)
+    assert bad == 0 and (st["status"] == 0).all(), (st, sto)
+    assert np.abs(V - Vo).max() < U_ATOL
+    assert (np.abs(st["objective"] - sto["f"]) <= OBJ_RTOL * np.abs(sto["f"])).all()
