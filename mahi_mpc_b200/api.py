@@ -233,7 +233,7 @@ class Model:
                                   _ptr(Fu)[0], _ptr(H)[0], mem, st))
         return g, Fx, Fu, H
 
-    def nlp_eval(self, V, p, lam_g=None, lam_f=1.0, device=0, want=("f", "g", "grad_f", "Fx", "Fu", "Hzz")):
+    def nlp_eval(self, V, p, lam_g=None, lam_f=1.0, device=0, want=("f", "g", "grad_f", "Fx", "Fu", "Hzz"), opts=None):
         """Batched nlp_f/nlp_g/nlp_grad_f/nlp_jac_g/nlp_hess_l. V (B,NV), p (B,np), lam_g (B,M)."""
         V, p, lam_g = _f64(V), _f64(p), _f64(lam_g)
         B = V.shape[0]
@@ -241,7 +241,7 @@ class Model:
         shapes = dict(f=(B,), g=(B, self.M), grad_f=(B, self.NV), Fx=(B, self.N, self.nx, self.nx),
                       Fu=(B, self.N, self.nx, self.nu), Hzz=(B, self.N, self.s, self.s))
         out = {k: (np.empty(shapes[k]) if k in want else None) for k in shapes}
-        _ck(lib().mmpc_nlp_eval(self._h, device, None, B, _ptr(V)[0], _ptr(p)[0], _ptr(lam_g)[0], float(lam_f),
+        _ck(lib().mmpc_nlp_eval(self._h, device, C.byref(opts) if opts else None, B, _ptr(V)[0], _ptr(p)[0], _ptr(lam_g)[0], float(lam_f),
                                 *[_ptr(out[k])[0] for k in ("f", "g", "grad_f", "Fx", "Fu", "Hzz")], MEM_HOST, None))
         return {k: v for k, v in out.items() if v is not None}
 

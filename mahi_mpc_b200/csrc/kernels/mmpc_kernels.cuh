@@ -89,11 +89,78 @@ __device__ __forceinline__ void step_linear(double h, const double* x, const dou
     }
 }
 
+// RK4 x `substeps` shooting interval with exact forward sensitivities (the MATLAB prototypes' integrator:
+// workingMPC_8_30_21.m:46-59, 4 RK4 sub-steps per interval; plant of examples/model_generate_example.cpp:207-213).
+//   WANT 0: F           1: F, Fx = dF/dx, Fu = dF/du
+// Second derivatives through the integrator are not formed: under RK4 the solvers use the Gauss-Newton part of the
+// Lagrangian Hessian, which reaches the same KKT point.
+template <class M, int WANT>
+__device__ void step_rk4(double h, int substeps, const double* x, const double* u, double* F, double* Fx, double* Fu) {
+    constexpr int NX = M::NX, NU = M::NU;
+    const double hs = h / (double)substeps;
+    double xs[NX], Sx[NX * NX], Su[NX * NU];
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) xs[i] = x[i];
+    if (WANT >= 1) {
+        MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) Sx[i] = (i / NX == i % NX) ? 1.0 : 0.0;
+        MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) Su[i] = 0.0;
+    }
+    for (int m = 0; m < substeps; ++m) {
+        double xa[NX], acc[NX], accx[NX * NX], accu[NX * NU], Tx[NX * NX], Tu[NX * NU];
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) { xa[i] = xs[i]; acc[i] = 0.0; }
+        if (WANT >= 1) {
+            MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) { Tx[i] = Sx[i]; accx[i] = 0.0; }
+            MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) { Tu[i] = Su[i]; accu[i] = 0.0; }
+        }
+#pragma unroll 1
+        for (int st = 0; st < 4; ++st) {
+            const double wgt = (st == 0 || st == 3) ? 1.0 / 6.0 : 1.0 / 3.0;   // RK4 weights
+            const double adv = (st == 2) ? 1.0 : 0.5;                          // next stage point = xs + adv*hs*k
+            double k[NX], kx[NX * NX], ku[NX * NU];
+            if (WANT == 0) {
+                M::f(xa, u, k);
+            } else {
+                double A[NX * NX], B[NX * NU];
+                M::fAB(xa, u, k, A, B);
+                MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+                    MMPC_UNROLL for (int j = 0; j < NX; ++j) {
+                        double t = 0.0;
+                        MMPC_UNROLL for (int l = 0; l < NX; ++l) t = fma(A[i * NX + l], Tx[l * NX + j], t);
+                        kx[i * NX + j] = t;
+                    }
+                    MMPC_UNROLL for (int j = 0; j < NU; ++j) {
+                        double t = B[i * NU + j];
+                        MMPC_UNROLL for (int l = 0; l < NX; ++l) t = fma(A[i * NX + l], Tu[l * NU + j], t);
+                        ku[i * NU + j] = t;
+                    }
+                }
+            }
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+                acc[i] = fma(wgt, k[i], acc[i]);
+                xa[i] = fma(adv * hs, k[i], xs[i]);
+            }
+            if (WANT >= 1) {
+                MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) { accx[i] = fma(wgt, kx[i], accx[i]); Tx[i] = fma(adv * hs, kx[i], Sx[i]); }
+                MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) { accu[i] = fma(wgt, ku[i], accu[i]); Tu[i] = fma(adv * hs, ku[i], Su[i]); }
+            }
+        }
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) xs[i] = fma(hs, acc[i], xs[i]);
+        if (WANT >= 1) {
+            MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) Sx[i] = fma(hs, accx[i], Sx[i]);
+            MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) Su[i] = fma(hs, accu[i], Su[i]);
+        }
+    }
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) F[i] = xs[i];
+    if (WANT >= 1) {
+        MMPC_UNROLL for (int i = 0; i < NX * NX; ++i) Fx[i] = Sx[i];
+        MMPC_UNROLL for (int i = 0; i < NX * NU; ++i) Fu[i] = Su[i];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // eval_nodes: n independent shooting nodes, SoA in / SoA out, one thread per node (HBM-bound stream)
 // ---------------------------------------------------------------------------------------------
 template <class M, bool WITH_H>
-__global__ void __launch_bounds__(128) eval_nodes_kernel(double h, long long n, const double* __restrict__ x,
+__global__ void __launch_bounds__(128) eval_nodes_kernel(double h, int rk4_substeps, long long n, const double* __restrict__ x,
                                                          const double* __restrict__ u, const double* __restrict__ xn,
                                                          const double* __restrict__ w, double* __restrict__ g,
                                                          double* __restrict__ Fx, double* __restrict__ Fu,
@@ -111,6 +178,8 @@ __global__ void __launch_bounds__(128) eval_nodes_kernel(double h, long long n, 
             }
             step_euler<M, 2>(h, xr, ur, zero, zero, wr, F, fx, fu, hs);
             MMPC_UNROLL for (int i = 0; i < NH; ++i) __stcs(&H[i * n + j], hs[i]);
+        } else if (rk4_substeps > 0) {
+            step_rk4<M, 1>(h, rk4_substeps, xr, ur, F, fx, fu);
         } else {
             step_euler<M, 1>(h, xr, ur, nullptr, nullptr, nullptr, F, fx, fu, nullptr);
         }
@@ -195,6 +264,9 @@ __global__ void __launch_bounds__(128) nlp_eval_kernel(mmpc_problem P, int B, co
             MMPC_UNROLL for (int c = 0; c < NU; ++c) Bm[rr * NU + c] = pv.B[c * NX + rr];
         }
         step_linear<M, 2>(P.h, x, u, A, Bm, pv.xdot_init, pv.x_init, pv.u_init, F, fx, fu, hs);
+    } else if (P.integrator == MMPC_RK4) {
+        step_rk4<M, 1>(P.h, P.substeps, x, u, F, fx, fu);
+        MMPC_UNROLL for (int i = 0; i < NH; ++i) hs[i] = 0.0;  // Gauss-Newton part only (no d2F through the integrator)
     } else {
         step_euler<M, 2>(P.h, x, u, wq, r, lam, F, fx, fu, hs);
     }
@@ -308,15 +380,16 @@ template <class M>
 struct Launch {
     static cudaError_t eval_nodes(const mmpc_problem& P, long long n, const double* x, const double* u, const double* xn,
                                   const double* w, double* g, double* Fx, double* Fu, double* H, cudaStream_t st, int* launches) {
-        if (P.integrator != MMPC_EULER || P.is_linear) return cudaErrorNotSupported;
+        if (P.is_linear || (P.integrator != MMPC_EULER && w)) return cudaErrorNotSupported;  // no second derivatives through RK4
         if (n <= 0) return cudaSuccess;
+        const int rk = P.integrator == MMPC_RK4 ? P.substeps : 0;
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const long long want = (n + 127) / 128;
         const int grid = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);  // grid-stride, multiple of the SM count
-        if (w) eval_nodes_kernel<M, true><<<grid, 128, 0, st>>>(P.h, n, x, u, xn, w, g, Fx, Fu, H);
-        else eval_nodes_kernel<M, false><<<grid, 128, 0, st>>>(P.h, n, x, u, xn, w, g, Fx, Fu, H);
+        if (w) eval_nodes_kernel<M, true><<<grid, 128, 0, st>>>(P.h, 0, n, x, u, xn, w, g, Fx, Fu, H);
+        else eval_nodes_kernel<M, false><<<grid, 128, 0, st>>>(P.h, rk, n, x, u, xn, w, g, Fx, Fu, H);
         if (launches) ++*launches;
         return cudaGetLastError();
     }
@@ -330,7 +403,7 @@ struct Launch {
     static cudaError_t nlp_eval(const mmpc_problem& P, int B, const double* V, const double* p, const double* lam, double lam_f,
                                 double* f, double* g, double* grad_f, double* Fx, double* Fu, double* Hzz, cudaStream_t st,
                                 int* launches) {
-        if (P.integrator != MMPC_EULER) return cudaErrorNotSupported;
+        if (P.integrator == MMPC_RK4 && P.is_linear) return cudaErrorNotSupported;
         if (B <= 0) return cudaSuccess;
         const int NV = M::NX * (P.N + 1) + M::NU * P.N;
         cudaError_t e;
@@ -378,9 +451,9 @@ struct Launch {
     extern "C" cudaError_t mmpc_solve_t3_##MODEL(const mmpc_problem*, const mmpc_workspace*, const mmpc_solve_io*, cudaStream_t); \
     static cudaError_t mmpc_solve_dispatch_##MODEL(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io,  \
                                                    cudaStream_t st, int* launches) {                                    \
-        if (P.integrator != MMPC_EULER) return cudaErrorNotSupported;                                                   \
-        /* bounds are implemented by T1 only (the ABI layer switches variants) */                                        \
-        if ((W.variant == 2 || W.variant == 3) && P.bounded) return cudaErrorNotSupported;                              \
+        if (P.integrator == MMPC_RK4 && P.is_linear) return cudaErrorNotSupported;                                      \
+        /* bounds and RK4 are implemented by T1 only (the ABI layer switches variants) */                                \
+        if ((W.variant == 2 || W.variant == 3) && (P.bounded || P.integrator != MMPC_EULER)) return cudaErrorNotSupported; \
         if (launches) ++*launches;                                                                                      \
         if (W.variant == 2) return mmpc_solve_t2_##MODEL(&P, &W, &io, st);                                              \
         if (W.variant == 3) return mmpc_solve_t3_##MODEL(&P, &W, &io, st);                                              \

@@ -374,3 +374,48 @@ def test_arm4_solve_vs_oracle(api, coracle, variant):
     assert bad == 0 and (st["status"] == 0).all(), (st, sto)
     assert np.abs(V - Vo).max() < U_ATOL
     assert (np.abs(st["objective"] - sto["f"]) <= OBJ_RTOL * np.abs(sto["f"])).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# RK4 x M shooting integrator (workingMPC_8_30_21.m:46-59): rollout + exact forward sensitivities;
+# the solve uses the Gauss-Newton part of the Hessian and must reach the same KKT point as the oracle.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("substeps", [1, 4])
+def test_rk4_rollout_and_jacobian_vs_oracle(api, substeps):
+    n = 513
+    x, u, xn, _ = random_nodes(n, 7 + substeps)
+    m = api.Model("double_pendulum", N=10, step_size_us=100000)  # dt = 0.1 s as in the MATLAB prototypes
+    P = nlp.Problem(N=10, h=0.1, integrator="rk4", substeps=substeps)
+    o = api.default_options(integrator=api.RK4, substeps=substeps)
+    g, Fx, Fu, H = m.eval_nodes(x.T.copy(), u.T.copy(), xn.T.copy(), opts=o)
+    F, Fxo, Fuo = P.step_jac(x, u, {})
+    assert H is None
+    assert rel(g.T, F - xn) < EVAL_RTOL and rel(Fx.T.reshape(n, 4, 4), Fxo) < EVAL_RTOL and rel(Fu.T.reshape(n, 4, 2), Fuo) < EVAL_RTOL
+    with pytest.raises(api.MmpcError):  # no second derivatives through the integrator
+        m.eval_nodes(x.T.copy(), u.T.copy(), xn.T.copy(), np.ones((4, n)), opts=o)
+
+
+def test_rk4_nlp_and_solve_vs_oracle(api):
+    N, B, h = 10, 3, 0.05
+    P = nlp.Problem(N=N, h=h, integrator="rk4", substeps=2)
+    Q, R, Rm = nlp.default_weights(4, 2)
+    x0, up, traj = nlp.synthetic_batch(4, 2, N, h, B)
+    p = np.stack([P.pack_p(traj[b], Q, R, Rm, up[b]) for b in range(B)])
+    m = api.Model("double_pendulum", N=N, step_size_us=int(h * 1e6))
+    rng = np.random.default_rng(11)
+    V = rng.uniform(-0.5, 0.5, (B, P.NV))
+    out = m.nlp_eval(V, p, None, opts=api.default_options(integrator=api.RK4, substeps=2), want=("f", "g", "grad_f", "Fx", "Fu"))
+    for b in range(B):
+        f, gf = P.nlp_grad_f(V[b], p[b])
+        g, J = P.nlp_jac_g(V[b], p[b])
+        assert abs(out["f"][b] - f) <= EVAL_RTOL * abs(f) and rel(out["g"][b], g) < EVAL_RTOL and rel(out["grad_f"][b], gf) < EVAL_RTOL
+        for k in range(N):
+            assert rel(out["Fx"][b, k], J[k * 4:(k + 1) * 4, k * 6:k * 6 + 4]) < EVAL_RTOL
+    s = api.Solver(m, B, tol=1e-9, integrator=api.RK4, substeps=2)
+    s.set_weights(Q, R, Rm)
+    Vs, lam, st = s.solve(x0, up, traj)
+    assert (st["status"] == 0).all(), st
+    for b in range(B):
+        r = nlp.solve(P, x0[b], p[b], tol=1e-10, max_iter=400)
+        assert r.status == 0
+        assert np.abs(Vs[b] - r.V).max() < U_ATOL and abs(st["objective"][b] - r.f) <= OBJ_RTOL * abs(r.f)
