@@ -174,6 +174,19 @@ int mmpc_reset_warm_start(mmpc_solver_t solver);
 int mmpc_solve(mmpc_solver_t solver, const double* state, const double* control, const double* traj, double* V_out,
                double* lam_out, mmpc_stats* stats, mmpc_mem mem, void* stream);
 
+/* Closed-loop simulation of `batch` independent control loops, device resident (the loops of
+ * examples/model_generate_example.cpp:156-230 and examples/model_control_example.cpp:54-93, batched): every cycle
+ * re-plans with mmpc_solve against the window [c, c+N) of the long reference, applies the first control of the plan
+ * and advances the plant one step_size with plant_integrator = MMPC_RK4 (model_generate_example.cpp:207-213) or
+ * MMPC_EULER (model_control_example.cpp:81-86).  No host synchronisation inside the loop.
+ *   state[B*nx], control[B*nu]      in: initial state / previous control; out: final ones
+ *   traj_long[B*(cycles+N-1)*nx]    reference samples r(t0 + m*step_size), m = 0..cycles+N-2
+ *   X_log[B*cycles*nx], U_log[B*cycles*nu]   state before each step and applied control (either may be NULL)
+ *   iters_log[B*cycles]             Newton iterations of every solve (may be NULL)
+ * The handle's warm start carries from cycle to cycle exactly as in ModelControl (ModelControl.cpp:161). */
+int mmpc_closed_loop(mmpc_solver_t solver, int cycles, int plant_integrator, double* state, double* control, const double* traj_long,
+                     double* X_log, double* U_log, int* iters_log, mmpc_mem mem, void* stream);
+
 /* Time of the device work of the last mmpc_solve on this handle in milliseconds (CUDA events on the
  * launching stream): [0] H2D staging, [1] kernels, [2] D2H staging. */
 int mmpc_last_timing(mmpc_solver_t solver, double ms[3]);

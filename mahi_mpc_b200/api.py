@@ -56,6 +56,7 @@ ABI_SYMBOLS = [
     "mmpc_model_op_counts", "mmpc_linearise", "mmpc_eval_nodes", "mmpc_nlp_eval", "mmpc_solver_create",
     "mmpc_solver_free", "mmpc_solver_batch", "mmpc_set_options", "mmpc_set_weights", "mmpc_set_bounds",
     "mmpc_reset_warm_start", "mmpc_solve", "mmpc_last_timing", "mmpc_last_launch_count", "mmpc_measure_fp64_peak",
+    "mmpc_closed_loop",
 ]
 
 _lib = None
@@ -93,6 +94,7 @@ def lib():
         L.mmpc_last_launch_count.argtypes = [vp, C.POINTER(C.c_int)]
         L.mmpc_device_count.argtypes = [C.POINTER(C.c_int)]
         L.mmpc_measure_fp64_peak.argtypes = [C.c_int, _dp]
+        L.mmpc_closed_loop.argtypes = [vp, C.c_int, C.c_int] + [vp] * 6 + [C.c_int, vp]
         _lib = L
     return _lib
 
@@ -309,6 +311,32 @@ class Solver:
         _ck(lib().mmpc_solve(self._h, _ptr(state)[0], _ptr(control)[0], _ptr(traj)[0], _ptr(V)[0], _ptr(lam)[0],
                              _ptr(st)[0], MEM_HOST, None))
         return V, lam, st
+
+    def closed_loop(self, state, control, traj_long, cycles, plant=RK4, want_logs=True):
+        """`cycles` closed-loop steps of every instance on the device. numpy (host) or torch CUDA (device) buffers.
+        state (B,nx), control (B,nu) are updated in place; traj_long (B, cycles+N-1, nx).
+        Returns X_log (B,cycles,nx), U_log (B,cycles,nu), iters (B,cycles) int32."""
+        m, B = self.model, self.batch
+        if _is_torch(state):
+            import torch
+            dev = state.device
+            X = torch.empty(B, cycles, m.nx, dtype=torch.float64, device=dev) if want_logs else None
+            U = torch.empty(B, cycles, m.nu, dtype=torch.float64, device=dev) if want_logs else None
+            it = torch.empty(B, cycles, dtype=torch.int32, device=dev) if want_logs else None
+            stream, _ = _stream_of(state)
+            _ck(lib().mmpc_closed_loop(self._h, int(cycles), int(plant), _ptr(state)[0], _ptr(control)[0], _ptr(traj_long)[0],
+                                       _ptr(X)[0], _ptr(U)[0], None if it is None else C.c_void_p(it.data_ptr()),
+                                       MEM_DEVICE if state.is_cuda else MEM_HOST, stream))
+            return X, U, it
+        assert state.dtype == np.float64 and state.flags["C_CONTIGUOUS"] and control.flags["C_CONTIGUOUS"]
+        traj_long = _f64(traj_long)
+        assert traj_long.shape == (B, cycles + m.N - 1, m.nx), traj_long.shape
+        X = np.empty((B, cycles, m.nx)) if want_logs else None
+        U = np.empty((B, cycles, m.nu)) if want_logs else None
+        it = np.empty((B, cycles), dtype=np.int32) if want_logs else None
+        _ck(lib().mmpc_closed_loop(self._h, int(cycles), int(plant), _ptr(state)[0], _ptr(control)[0], _ptr(traj_long)[0],
+                                   _ptr(X)[0], _ptr(U)[0], None if it is None else C.c_void_p(it.ctypes.data), MEM_HOST, None))
+        return X, U, it
 
     def last_timing(self):
         t = (C.c_double * 3)()

@@ -205,6 +205,25 @@ __global__ void linearise_kernel(int n, const double* __restrict__ x, const doub
     if (B) MMPC_UNROLL for (int r = 0; r < NX; ++r) MMPC_UNROLL for (int c = 0; c < NU; ++c) B[(size_t)j * NX * NU + c * NX + r] = b[r * NU + c];
 }
 
+// plant of the closed-loop drivers: one thread per instance applies u_0 of its plan for one step
+template <class M>
+__global__ void plant_step_kernel(int B, int N, double h, int rk4, const double* __restrict__ V, double* __restrict__ state,
+                                  double* __restrict__ control, double* __restrict__ X_log, double* __restrict__ U_log, int cycle, int cycles) {
+    constexpr int NX = M::NX, NU = M::NU;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const size_t NV = (size_t)NX * (N + 1) + (size_t)NU * N;
+    double x[NX], u[NU], F[NX];
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) x[i] = state[(size_t)b * NX + i];
+    MMPC_UNROLL for (int j = 0; j < NU; ++j) u[j] = V[(size_t)b * NV + NX + j];  // first move of the plan (ModelControl.cpp:179-183)
+    if (X_log) MMPC_UNROLL for (int i = 0; i < NX; ++i) X_log[((size_t)b * cycles + cycle) * NX + i] = x[i];
+    if (U_log) MMPC_UNROLL for (int j = 0; j < NU; ++j) U_log[((size_t)b * cycles + cycle) * NU + j] = u[j];
+    if (rk4) step_rk4<M, 0>(h, 1, x, u, F, nullptr, nullptr);
+    else step_euler<M, 0>(h, x, u, nullptr, nullptr, nullptr, F, nullptr, nullptr, nullptr);
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) state[(size_t)b * NX + i] = F[i];
+    MMPC_UNROLL for (int j = 0; j < NU; ++j) control[(size_t)b * NU + j] = u[j];
+}
+
 // ---------------------------------------------------------------------------------------------
 // views of the reference's parameter vector p (ModelGenerator.cpp:129-187)
 // ---------------------------------------------------------------------------------------------
@@ -414,6 +433,13 @@ struct Launch {
         if (launches) ++*launches;
         return cudaGetLastError();
     }
+    static cudaError_t plant_step(int B, int N, double h, int plant_integrator, const double* V, double* state, double* control,
+                                  double* X_log, double* U_log, int cycle, int cycles, cudaStream_t st, int* launches) {
+        if (B <= 0) return cudaSuccess;
+        plant_step_kernel<M><<<(B + 127) / 128, 128, 0, st>>>(B, N, h, plant_integrator == MMPC_RK4, V, state, control, X_log, U_log, cycle, cycles);
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
     // per-variant launchers; each may live in its own translation unit (MMPC_DEFINE_SOLVE_T*)
     static cudaError_t solve_t1(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         if (P.bounded) solve_kernel_t1<M, true><<<(W.B + 31) / 32, 32, 0, st>>>(P, W, io);
@@ -464,7 +490,8 @@ struct Launch {
         static const mmpc_model_vtable vt = {MMPC_VTABLE_VERSION, M::MODEL_NAME, M::NX, M::NU,                           \
                                              {M::OPS_F, M::TRANS_F, M::OPS_FAB, M::TRANS_FAB, M::OPS_FABH, M::TRANS_FABH}, \
                                              &mmpc::Launch<M>::eval_nodes, &mmpc::Launch<M>::linearise,                  \
-                                             &mmpc::Launch<M>::nlp_eval, &mmpc_solve_dispatch_##MODEL};                  \
+                                             &mmpc::Launch<M>::nlp_eval, &mmpc_solve_dispatch_##MODEL,                   \
+                                             &mmpc::Launch<M>::plant_step};                                              \
         return &vt;                                                                                                      \
     }
 // everything in one unit (what ModelGenerator::generate_c_code emits for a user model)

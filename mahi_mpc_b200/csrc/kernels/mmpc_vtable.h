@@ -6,7 +6,7 @@
 
 #define MMPC_MAXNX 16
 #define MMPC_MAXNU 8
-#define MMPC_VTABLE_VERSION 3
+#define MMPC_VTABLE_VERSION 4
 
 struct mmpc_stats;  // public struct (include/mahi_mpc_b200.h)
 
@@ -81,6 +81,11 @@ struct mmpc_model_vtable {
                             int* launches);
     cudaError_t (*solve)(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st,
                          int* launches);
+    // plant of the closed-loop drivers: apply the first control of each plan V for one step of length h
+    // (plant_integrator MMPC_EULER: examples/model_control_example.cpp:81-86, MMPC_RK4: model_generate_example.cpp:207-213);
+    // logs the state before the step and the applied control at log slot `cycle` of `cycles`.
+    cudaError_t (*plant_step)(int B, int N, double h, int plant_integrator, const double* V, double* state, double* control,
+                              double* X_log, double* U_log, int cycle, int cycles, cudaStream_t st, int* launches);
 };
 
 extern "C" typedef const mmpc_model_vtable* (*mmpc_vtable_getter)(void);

@@ -419,3 +419,38 @@ def test_rk4_nlp_and_solve_vs_oracle(api):
         r = nlp.solve(P, x0[b], p[b], tol=1e-10, max_iter=400)
         assert r.status == 0
         assert np.abs(Vs[b] - r.V).max() < U_ATOL and abs(st["objective"][b] - r.f) <= OBJ_RTOL * abs(r.f)
+
+
+@pytest.mark.parametrize("plant", ["rk4", "euler"])
+def test_closed_loop_batch_vs_oracle(api, coracle, plant):
+    """device-resident closed loop (solve -> apply u_0 -> plant step) for a batch, against the same loop
+    driven on the host with the ORACLE's solver and plant."""
+    from oracle import models
+    N, B, cycles, h = 25, 6, 15, 0.002
+    P = nlp.Problem(N=N)
+    Q, R, Rm = nlp.default_weights(4, 2)
+    x0, up, traj_long = nlp.synthetic_batch(4, 2, cycles + N - 1, h, B, offset=77)
+    mdl = models.numeric("double_pendulum")
+    f = lambda x, u: mdl["f"](x.T, u.T).T
+    # oracle loop (host): warm start carried like ModelControl.cpp:161
+    x, u, V0 = x0.copy(), up.copy(), None
+    Xo, Uo = np.empty((B, cycles, 4)), np.empty((B, cycles, 2))
+    for c in range(cycles):
+        p = np.stack([P.pack_p(traj_long[b, c:c + N], Q, R, Rm, u[b]) for b in range(B)])
+        V0, _, st, bad = coracle.solve_batch("double_pendulum", N, h, False, x, p, V0=V0, tol=1e-11)
+        assert bad == 0
+        u = V0[:, 4:6].copy()
+        Xo[:, c], Uo[:, c] = x, u
+        if plant == "rk4":
+            k1 = f(x, u); k2 = f(x + h / 2 * k1, u); k3 = f(x + h / 2 * k2, u); k4 = f(x + h * k3, u)
+            x = x + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        else:
+            x = x + h * f(x, u)
+    m = api.Model("double_pendulum", N=N)
+    s = api.Solver(m, B, tol=1e-10)
+    s.set_weights(Q, R, Rm)
+    xs, us = x0.copy(), up.copy()
+    X, U, it = s.closed_loop(xs, us, traj_long, cycles, plant=api.RK4 if plant == "rk4" else api.EULER)
+    assert np.abs(U - Uo).max() < U_ATOL and np.abs(X - Xo).max() < 1e-8
+    assert np.abs(xs - x).max() < 1e-8 and np.abs(us - u).max() < U_ATOL  # final state / control written back
+    assert (it[:, 1:] <= it[:, :1]).all() and (it >= 0).all()             # warm starts never need more than the cold solve
