@@ -159,7 +159,7 @@ __device__ void step_rk4(double h, int substeps, const double* x, const double* 
 // ---------------------------------------------------------------------------------------------
 // eval_nodes: n independent shooting nodes, SoA in / SoA out, one thread per node (HBM-bound stream)
 // ---------------------------------------------------------------------------------------------
-template <class M, bool WITH_H>
+template <class M, bool WITH_H, bool RK4>
 __global__ void __launch_bounds__(128) eval_nodes_kernel(double h, int rk4_substeps, long long n, const double* __restrict__ x,
                                                          const double* __restrict__ u, const double* __restrict__ xn,
                                                          const double* __restrict__ w, double* __restrict__ g,
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(128) eval_nodes_kernel(double h, int rk4_subst
             }
             step_euler<M, 2>(h, xr, ur, zero, zero, wr, F, fx, fu, hs);
             MMPC_UNROLL for (int i = 0; i < NH; ++i) __stcs(&H[i * n + j], hs[i]);
-        } else if (rk4_substeps > 0) {
+        } else if (RK4) {  // separate instantiation: keeps the Euler streaming kernel at its low register count
             step_rk4<M, 1>(h, rk4_substeps, xr, ur, F, fx, fu);
         } else {
             step_euler<M, 1>(h, xr, ur, nullptr, nullptr, nullptr, F, fx, fu, nullptr);
@@ -407,8 +407,9 @@ struct Launch {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const long long want = (n + 127) / 128;
         const int grid = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);  // grid-stride, multiple of the SM count
-        if (w) eval_nodes_kernel<M, true><<<grid, 128, 0, st>>>(P.h, 0, n, x, u, xn, w, g, Fx, Fu, H);
-        else eval_nodes_kernel<M, false><<<grid, 128, 0, st>>>(P.h, rk, n, x, u, xn, w, g, Fx, Fu, H);
+        if (w) eval_nodes_kernel<M, true, false><<<grid, 128, 0, st>>>(P.h, 0, n, x, u, xn, w, g, Fx, Fu, H);
+        else if (rk) eval_nodes_kernel<M, false, true><<<grid, 128, 0, st>>>(P.h, rk, n, x, u, xn, w, g, Fx, Fu, H);
+        else eval_nodes_kernel<M, false, false><<<grid, 128, 0, st>>>(P.h, 0, n, x, u, xn, w, g, Fx, Fu, H);
         if (launches) ++*launches;
         return cudaGetLastError();
     }
