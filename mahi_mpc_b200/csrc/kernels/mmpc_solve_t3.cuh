@@ -16,15 +16,19 @@
 //   * the two run concurrently on double-buffered records: one __syncthreads per chunk, no other synchronisation.
 // One launch per batched solve; no grid-wide synchronisation.  Replaces IPOPT+MUMPS at ModelControl.cpp:159.
 #pragma once
+#ifdef MMPC_T3_PROFILE
+#include <cstdio>
+#endif
 
 namespace mmpc {
 
-template <class M, int I_>
+template <class M, int I_, int CB_, int CF_>
 struct T3 {
     static constexpr int NX = M::NX, NU = M::NU, S = NX + NU, N2 = NX + 2 * NU, NH = S * (S + 1) / 2;
-    static constexpr int I = I_;  // instances per CTA (<= 32: one serial lane each)
-    static constexpr int C = 4;   // nodes per chunk
-    static constexpr int WORKERS = I * C;
+    static constexpr int I = I_;    // instances per CTA (<= 32: one serial lane each)
+    static constexpr int CB = CB_;  // nodes per chunk in the backward sweep (one node per worker thread)
+    static constexpr int CF = CF_;  // nodes per chunk in the forward sweep (CF <= CB)
+    static constexpr int WORKERS = I * CB;
     static constexpr int THREADS = 32 + WORKERS;
     // backward record fields (shared): Fx | Fu | H (packed full stage Hessian) | c | q~ = (qx, qv, qu)
     static constexpr int RB_FX = 0, RB_FU = RB_FX + NX * NX, RB_H = RB_FU + NX * NU, RB_C = RB_H + NH, RB_Q = RB_C + NX, RB = RB_Q + N2;
@@ -34,10 +38,9 @@ struct T3 {
     static constexpr int PG_XX = 0, PG_XV = NX * NX, PG_X = PG_XV + NX * NU, PG = PG_X + NX;
     // forward record (shared) = FG | KG | PG
     static constexpr int RF_K = FG, RF_P = FG + KG, RF = FG + KG + PG;
-    static constexpr int REC = RB > RF ? RB : RF;
-    static constexpr int BUF = C * REC * I;  // one record buffer (two are used)
+    static constexpr int BUF = (CB * RB > CF * RF ? CB * RB : CF * RF) * I;  // one record buffer (two are used)
     static constexpr int NRED = 5;           // per-(node,instance) reduction slots
-    static constexpr int REDBUF = NRED * C * I;
+    static constexpr int REDBUF = NRED * CB * I;
     static constexpr int SM_REC = 0, SM_RED = 2 * BUF, SM_INST = SM_RED + 2 * REDBUF, SM_END = SM_INST + 4 * I;
     static constexpr size_t SMEM_BYTES = sizeof(double) * SM_END;
     static constexpr int LIN = NX * NX + NX * NU + NX;
@@ -146,11 +149,11 @@ __device__ __noinline__ void t3_eval_node(const T3Ctx<M>& cin, int k, int i, int
     }
 #undef T3_REC
 #undef T3_FG
-    red[(0 * C::C + j) * I + i] = dual;
-    red[(1 * C::C + j) * I + i] = prim;
-    red[(2 * C::C + j) * I + i] = theta;
-    red[(3 * C::C + j) * I + i] = fval;
-    red[(4 * C::C + j) * I + i] = lam1;
+    red[(0 * C::CB + j) * I + i] = dual;
+    red[(1 * C::CB + j) * I + i] = prim;
+    red[(2 * C::CB + j) * I + i] = theta;
+    red[(3 * C::CB + j) * I + i] = fval;
+    red[(4 * C::CB + j) * I + i] = lam1;
 }
 
 // ---- serial phase of the backward sweep: one lane per instance, T1's Riccati update on the augmented state -----
@@ -298,32 +301,45 @@ __device__ __noinline__ bool t3_backward(const T3Ctx<M>& c, double* smem, int ti
     if (tid < I) dl[tid] = delta_self;
     __syncthreads();
     const double delta = worker ? dl[wi] : 0.0;
-    const int nch = (N + C::C - 1) / C::C;
+    const int nch = (N + C::CB - 1) / C::CB;
     auto eval_chunk = [&](int ch) {
-        const int k0 = ch * C::C, kn = min(C::C, N - k0);
+        const int k0 = ch * C::CB, kn = min(C::CB, N - k0);
         if (wj < kn) t3_eval_node<M, C>(c, k0 + wj, wi, wj, delta, smem + C::SM_REC + (ch & 1) * C::BUF, smem + C::SM_RED + (ch & 1) * C::REDBUF, fg_tile);
     };
+#ifdef MMPC_T3_PROFILE
+    long long t_work = 0, t_all0 = clock64();
+#endif
     if (worker) eval_chunk(nch - 1);
     __syncthreads();
     for (int ch = nch - 1; ch >= 0; --ch) {
+#ifdef MMPC_T3_PROFILE
+        const long long t0 = clock64();
+#endif
         if (worker) {
             if (ch > 0) eval_chunk(ch - 1);
         } else if (tid < I) {
-            const int k0 = ch * C::C, kn = min(C::C, N - k0);
+            const int k0 = ch * C::CB, kn = min(C::CB, N - k0);
             const double* rec = smem + C::SM_REC + (ch & 1) * C::BUF;
             const double* red = smem + C::SM_RED + (ch & 1) * C::REDBUF;
             for (int s = kn - 1; s >= 0; --s) {
                 const int k = k0 + s;
                 ok = t3_riccati_stage<M, C>(V, rec, s, tid, c.R, kg_tile + (size_t)k * C::KG * I + tid, pg_tile + (size_t)k * C::PG * I + tid) && ok;
-                nrm.dual_inf = fmax(nrm.dual_inf, red[(0 * C::C + s) * I + tid]);
-                nrm.prim_inf = fmax(nrm.prim_inf, red[(1 * C::C + s) * I + tid]);
-                nrm.theta += red[(2 * C::C + s) * I + tid];
-                nrm.fval += red[(3 * C::C + s) * I + tid];
-                nrm.lam_l1 += red[(4 * C::C + s) * I + tid];
+                nrm.dual_inf = fmax(nrm.dual_inf, red[(0 * C::CB + s) * I + tid]);
+                nrm.prim_inf = fmax(nrm.prim_inf, red[(1 * C::CB + s) * I + tid]);
+                nrm.theta += red[(2 * C::CB + s) * I + tid];
+                nrm.fval += red[(3 * C::CB + s) * I + tid];
+                nrm.lam_l1 += red[(4 * C::CB + s) * I + tid];
             }
         }
+#ifdef MMPC_T3_PROFILE
+        t_work += clock64() - t0;
+#endif
         __syncthreads();
     }
+#ifdef MMPC_T3_PROFILE
+    if (blockIdx.x == 0 && (tid == 0 || tid == 32))
+        printf("[t3 backward] tid %d busy %lld of %lld cycles (%d chunks of %d)\n", tid, t_work, clock64() - t_all0, nch, C::CB);
+#endif
     return ok;
 }
 
@@ -375,9 +391,9 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M>& c, double* smem, int tid
     MMPC_UNROLL for (int a = 0; a < NU; ++a) dv[a] = 0.0;
     o.gradf_d = o.lam_inf = o.f1 = o.th1 = 0.0;
     o.finite = true;
-    const int nch = (N + C::C - 1) / C::C;
+    const int nch = (N + C::CF - 1) / C::CF;
     auto stage_chunk = [&](int ch) {  // [node][field][instance] blocks are contiguous in the tile arrays
-        const int k0 = ch * C::C, kn = min(C::C, N - k0);
+        const int k0 = ch * C::CF, kn = min(C::CF, N - k0);
         double* buf = smem + C::SM_REC + (ch & 1) * C::BUF;
         for (int s = 0; s < kn; ++s) {
             const double* fg = fg_tile + (size_t)(k0 + s) * C::FG * I;
@@ -390,22 +406,28 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M>& c, double* smem, int tid
         }
     };
     double f1 = 0.0, th1 = 0.0;  // worker-local merit sums
-    auto trial_chunk = [&](int ch) {
-        const int k0 = ch * C::C, kn = min(C::C, N - k0);
+    auto trial_chunk = [&](int ch) {  // workers with node slot < CF take part
+        const int k0 = ch * C::CF, kn = min(C::CF, N - k0);
         if (wj < kn) t3_trial_node<M>(c, k0 + wj, 1.0, f1, th1);
     };
+#ifdef MMPC_T3_PROFILE
+    long long t_work = 0, t_all0 = clock64();
+#endif
     if (worker) {
         stage_chunk(0);
         cp_async_wait_all();
     }
     __syncthreads();
     for (int ch = 0; ch < nch; ++ch) {
+#ifdef MMPC_T3_PROFILE
+        const long long t0 = clock64();
+#endif
         if (worker) {
             if (ch + 1 < nch) stage_chunk(ch + 1);
             if (ch > 0) trial_chunk(ch - 1);
             cp_async_wait_all();
         } else if (tid < I) {
-            const int k0 = ch * C::C, kn = min(C::C, N - k0);
+            const int k0 = ch * C::CF, kn = min(C::CF, N - k0);
             const double* rec = smem + C::SM_REC + (ch & 1) * C::BUF;
             for (int s = 0; s < kn; ++s) {
                 const int k = k0 + s;
@@ -444,17 +466,24 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M>& c, double* smem, int tid
                 MMPC_UNROLL for (int a = 0; a < NU; ++a) dv[a] = du[a];
             }
         }
+#ifdef MMPC_T3_PROFILE
+        t_work += clock64() - t0;
+#endif
         __syncthreads();  // the step of chunk ch is visible to the workers; buffer (ch+1)&1 is staged
     }
+#ifdef MMPC_T3_PROFILE
+    if (blockIdx.x == 0 && (tid == 0 || tid == 32))
+        printf("[t3 forward ] tid %d busy %lld of %lld cycles (%d chunks of %d)\n", tid, t_work, clock64() - t_all0, nch, C::CF);
+#endif
     if (worker) {
         trial_chunk(nch - 1);
-        red[(0 * C::C + wj) * I + wi] = f1;
-        red[(1 * C::C + wj) * I + wi] = th1;
+        red[(0 * C::CB + wj) * I + wi] = f1;
+        red[(1 * C::CB + wj) * I + wi] = th1;
     }
     __syncthreads();
-    if (tid < I) MMPC_UNROLL for (int s = 0; s < C::C; ++s) {
-        o.f1 += red[(0 * C::C + s) * I + tid];
-        o.th1 += red[(1 * C::C + s) * I + tid];
+    if (tid < I) MMPC_UNROLL for (int s = 0; s < C::CF; ++s) {
+        o.f1 += red[(0 * C::CB + s) * I + tid];
+        o.th1 += red[(1 * C::CB + s) * I + tid];
     }
     __syncthreads();
 }
@@ -469,22 +498,22 @@ __device__ __noinline__ void t3_trial(const T3Ctx<M>& c, double* smem, int tid, 
     if (worker) {
         const double alpha = smem[C::SM_INST + I + wi];
         double a1 = 0.0, a2 = 0.0;
-        for (int k = wj; k < c.N; k += C::C) t3_trial_node<M>(c, k, alpha, a1, a2);
-        red[(0 * C::C + wj) * I + wi] = a1;
-        red[(1 * C::C + wj) * I + wi] = a2;
+        for (int k = wj; k < c.N; k += C::CB) t3_trial_node<M>(c, k, alpha, a1, a2);
+        red[(0 * C::CB + wj) * I + wi] = a1;
+        red[(1 * C::CB + wj) * I + wi] = a2;
     }
     __syncthreads();
     f1 = 0.0; th1 = 0.0;
-    if (tid < I) MMPC_UNROLL for (int s = 0; s < C::C; ++s) {
-        f1 += red[(0 * C::C + s) * I + tid];
-        th1 += red[(1 * C::C + s) * I + tid];
+    if (tid < I) MMPC_UNROLL for (int s = 0; s < C::CB; ++s) {
+        f1 += red[(0 * C::CB + s) * I + tid];
+        th1 += red[(1 * C::CB + s) * I + tid];
     }
     __syncthreads();
 }
 
-template <class M, int I_>
-__global__ void __launch_bounds__(T3<M, I_>::THREADS) solve_kernel_t3(mmpc_problem P, mmpc_workspace W, mmpc_solve_io io) {
-    using C = T3<M, I_>;
+template <class M, int I_, int CB_, int CF_>
+__global__ void __launch_bounds__(T3<M, I_, CB_, CF_>::THREADS) solve_kernel_t3(mmpc_problem P, mmpc_workspace W, mmpc_solve_io io) {
+    using C = T3<M, I_, CB_, CF_>;
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, tile = blockIdx.x;
@@ -515,9 +544,9 @@ __global__ void __launch_bounds__(T3<M, I_>::THREADS) solve_kernel_t3(mmpc_probl
     // ---- start point (ModelControl.cpp:28-50,68 cold; :161 warm), x_0 pinned (:144-145); the C workers of an instance help ----
     const bool warm = io.warm_start && W.have_warm;
     if (worker) {
-        if (!warm) for (int e = NX + j; e < NV; e += C::C) c.V[e] = 0.0;
-        if (!(warm && io.warm_start_duals)) for (int e = j; e < Mc; e += C::C) c.LAM[e] = 0.0;
-        for (int e = j; e < NX; e += C::C) {
+        if (!warm) for (int e = NX + j; e < NV; e += C::CB) c.V[e] = 0.0;
+        if (!(warm && io.warm_start_duals)) for (int e = j; e < Mc; e += C::CB) c.LAM[e] = 0.0;
+        for (int e = j; e < NX; e += C::CB) {
             c.V[e] = io.state[(size_t)bi * NX + e];
             c.DV[e] = 0.0;
         }
@@ -540,6 +569,9 @@ __global__ void __launch_bounds__(T3<M, I_>::THREADS) solve_kernel_t3(mmpc_probl
     double* sh_alpha = smem + C::SM_INST + I;      // per-instance step length
     double* sh_flag = smem + C::SM_INST + 2 * I;   // per-instance "apply the step" flag
     const int nfree = N * S, ncon = N * NX;
+#ifdef MMPC_T3_PROFILE
+    const long long t_kernel0 = clock64();
+#endif
     for (it = 0;; ++it) {
         T3Norms nrm;
         double delta = 0.0;
@@ -595,24 +627,27 @@ __global__ void __launch_bounds__(T3<M, I_>::THREADS) solve_kernel_t3(mmpc_probl
         if (worker && sh_flag[i] != 0.0) {  // the C workers of an instance update its iterate together, loads batched
             const double al = sh_alpha[i];
             constexpr int UB = 8;
-            for (int e0 = NX + j; e0 < NV; e0 += C::C * UB) {
+            for (int e0 = NX + j; e0 < NV; e0 += C::CB * UB) {
                 double vz[UB], vd[UB];
-                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::C < NV) { vz[q] = c.V[e0 + q * C::C]; vd[q] = c.DV[e0 + q * C::C]; }
-                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::C < NV) c.V[e0 + q * C::C] = fma(al, vd[q], vz[q]);
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) { vz[q] = c.V[e0 + q * C::CB]; vd[q] = c.DV[e0 + q * C::CB]; }
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) c.V[e0 + q * C::CB] = fma(al, vd[q], vz[q]);
             }
-            for (int e0 = j; e0 < Mc; e0 += C::C * UB) {
+            for (int e0 = j; e0 < Mc; e0 += C::CB * UB) {
                 double vl[UB], vn[UB];
-                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::C < Mc) { vl[q] = c.LAM[e0 + q * C::C]; vn[q] = c.LAMN[e0 + q * C::C]; }
-                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::C < Mc) c.LAM[e0 + q * C::C] = fma(al, vn[q] - vl[q], vl[q]);
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) { vl[q] = c.LAM[e0 + q * C::CB]; vn[q] = c.LAMN[e0 + q * C::CB]; }
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) c.LAM[e0 + q * C::CB] = fma(al, vn[q] - vl[q], vl[q]);
             }
         }
         __syncthreads();
     }
+#ifdef MMPC_T3_PROFILE
+    if (blockIdx.x == 0 && tid == 0) printf("[t3 kernel  ] loop %lld cycles, %d iterations\n", clock64() - t_kernel0, it);
+#endif
     // ---- outputs: the iterate already is the reference's V layout ----
     if (valid && worker) {
         double* Vo = io.V_out + (size_t)b * NV;
-        for (int e = j; e < NV; e += C::C) Vo[e] = c.V[e];
-        if (io.lam_out) for (int e = j; e < Mc; e += C::C) io.lam_out[(size_t)b * Mc + e] = c.LAM[e];
+        for (int e = j; e < NV; e += C::CB) Vo[e] = c.V[e];
+        if (io.lam_out) for (int e = j; e < Mc; e += C::CB) io.lam_out[(size_t)b * Mc + e] = c.LAM[e];
     }
     if (valid && tid < I && io.stats) {
         mmpc_stats s;
@@ -624,24 +659,28 @@ __global__ void __launch_bounds__(T3<M, I_>::THREADS) solve_kernel_t3(mmpc_probl
 
 template <class M>
 struct LaunchT3 {
-    template <int I_>
+    template <int I_, int CB_, int CF_>
     static cudaError_t go(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
-        using C = T3<M, I_>;
+        using C = T3<M, I_, CB_, CF_>;
         static bool attr_done = false;
         if (!attr_done && C::SMEM_BYTES > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(solve_kernel_t3<M, I_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+            cudaError_t e = cudaFuncSetAttribute(solve_kernel_t3<M, I_, CB_, CF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
             if (e != cudaSuccess) return e;
             attr_done = true;
         }
         const int grid = (W.B + C::I - 1) / C::I;
-        solve_kernel_t3<M, I_><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(P, W, io);
+        solve_kernel_t3<M, I_, CB_, CF_><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(P, W, io);
         return cudaGetLastError();
     }
+    // Configurations (tile width I, backward chunk CB, forward chunk CF):
+    //   A  8 x 4 x 4   64 threads, 41 KB: 4 CTAs/SM -- small batches, lowest latency
+    //   B 14 x 8 x 4  144 threads, 111 KB: 2 CTAs/SM -- wider backward chunks so that 8 Riccati stages cover the latency
+    //                  of one node evaluation in the worker warps
+    // kernel_variant = 3 + 256*k forces configuration k (1 = A, 2 = B) for experiments.
     static cudaError_t run(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
-        // tile width: 8 instances per CTA measured faster than 32 at the benchmark batch (more, smaller CTAs overlap their
-        // serial and worker phases better); kernel_variant = 3 + 256*32 selects the 32-wide tile for experiments
         const int forced = io.variant >> 8;
-        return forced == 32 ? go<32>(P, W, io, st) : go<8>(P, W, io, st);
+        const int cfg = forced ? forced : 1;
+        return cfg == 2 ? go<14, 8, 4>(P, W, io, st) : go<8, 4, 4>(P, W, io, st);
     }
 };
 
