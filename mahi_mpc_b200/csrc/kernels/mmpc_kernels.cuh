@@ -443,8 +443,9 @@ struct Launch {
     }
     // per-variant launchers; each may live in its own translation unit (MMPC_DEFINE_SOLVE_T*)
     static cudaError_t solve_t1(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
-        if (P.bounded) solve_kernel_t1<M, true><<<(W.B + 31) / 32, 32, 0, st>>>(P, W, io);
-        else solve_kernel_t1<M, false><<<(W.B + 31) / 32, 32, 0, st>>>(P, W, io);
+        const int grid = (io.b1 - io.b0 + 31) / 32;
+        if (P.bounded) solve_kernel_t1<M, true><<<grid, 32, 0, st>>>(P, W, io);
+        else solve_kernel_t1<M, false><<<grid, 32, 0, st>>>(P, W, io);
         return cudaGetLastError();
     }
     static cudaError_t solve_t2(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {

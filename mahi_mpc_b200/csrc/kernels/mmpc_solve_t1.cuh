@@ -477,8 +477,8 @@ __device__ __forceinline__ double z_safeguard(double z, double s, double mu) { r
 template <class M, bool BOUNDED>
 __global__ void __launch_bounds__(32) solve_kernel_t1(mmpc_problem P, mmpc_workspace W, mmpc_solve_io io) {
     constexpr int NX = M::NX, NU = M::NU, S = NX + NU;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= W.B) return;
+    const int b = io.b0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= io.b1) return;
     const int N = P.N;
     SolveCtx<M> c(P, W, io, b);
     MMPC_UNROLL for (int i = 0; i < NX; ++i) c.Q[i] = c.ld(W.Qw, i);

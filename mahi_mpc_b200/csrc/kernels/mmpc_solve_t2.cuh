@@ -422,10 +422,10 @@ __global__ void __launch_bounds__(32 * WARPS) solve_kernel_t2(mmpc_problem P, mm
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const int gl = lane % G, gw = lane / G;
     const int N = P.N, NV = NX * (N + 1) + NU * N, Mc = N * NX;
-    const int inst_raw = (blockIdx.x * WARPS + wic) * GPW + gw;
-    const bool valid = inst_raw < W.B;
+    const int inst_raw = io.b0 + (blockIdx.x * WARPS + wic) * GPW + gw;
+    const bool valid = inst_raw < io.b1;
     const int b = inst_raw;                          // workspace slot (arrays are sized for the padded batch)
-    const int bi = valid ? inst_raw : W.B - 1;       // surplus groups read the last instance's inputs, never write outputs
+    const int bi = valid ? inst_raw : io.b1 - 1;     // surplus groups read the last instance's inputs, never write outputs
 
     T2Ctx<M> c(P);
     c.N = N; c.gl = gl;
@@ -555,7 +555,7 @@ struct LaunchT2 {
             attr_done = true;
         }
         const int per_cta = WARPS * C::GPW;
-        const int grid = (W.B + per_cta - 1) / per_cta;
+        const int grid = (io.b1 - io.b0 + per_cta - 1) / per_cta;
         solve_kernel_t2<M, WARPS><<<grid, 32 * WARPS, smem, st>>>(P, W, io);
         return cudaGetLastError();
     }

@@ -516,15 +516,15 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_>::THREADS) solve_kernel_t3(
     using C = T3<M, I_, CB_, CF_>;
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
     extern __shared__ __align__(16) double smem[];
-    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int tid = threadIdx.x, tile = io.b0 / C::I + blockIdx.x;  // b0 is a multiple of 32*I-compatible tile starts
     const bool worker = tid >= 32;
     // a thread's instance: serial lane tid -> instance tid; worker w -> instance w % I (node slot w / I)
     const int i = worker ? (tid - 32) % I : (tid < I ? tid : 0);
     const int j = worker ? (tid - 32) / I : 0;
     const int N = P.N, NV = NX * (N + 1) + NU * N, Mc = N * NX;
     const int b = tile * I + i;                 // workspace slot (arrays are sized for the batch padded to 32)
-    const bool valid = b < W.B;
-    const int bi = valid ? b : W.B - 1;         // surplus slots read the last instance's inputs and never write outputs
+    const bool valid = b >= io.b0 && b < io.b1;
+    const int bi = valid ? b : io.b1 - 1;       // surplus slots read the last instance's inputs and never write outputs
 
     T3Ctx<M> c(P);
     c.N = N;
@@ -668,7 +668,8 @@ struct LaunchT3 {
             if (e != cudaSuccess) return e;
             attr_done = true;
         }
-        const int grid = (W.B + C::I - 1) / C::I;
+        const int t0 = io.b0 / C::I, t1 = (io.b1 + C::I - 1) / C::I;  // tiles touched by [b0, b1)
+        const int grid = t1 - t0;
         solve_kernel_t3<M, I_, CB_, CF_><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(P, W, io);
         return cudaGetLastError();
     }

@@ -6,7 +6,7 @@
 
 #define MMPC_MAXNX 16
 #define MMPC_MAXNU 8
-#define MMPC_VTABLE_VERSION 4
+#define MMPC_VTABLE_VERSION 5
 
 struct mmpc_stats;  // public struct (include/mahi_mpc_b200.h)
 
@@ -64,6 +64,7 @@ struct mmpc_solve_io {
     mmpc_stats* stats;                     // device pointer (B) or null
     double tol, mu_init;
     int max_iter, warm_start, warm_start_duals, variant;
+    int b0, b1;  // instance range [b0, b1) of this launch (b0 a multiple of 32): lets the ABI layer pipeline sub-batches
 };
 
 struct mmpc_model_vtable {
