@@ -108,3 +108,15 @@ def test_control_driver_closed_loop_vs_oracle(generated_model, examples):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     gl = np.loadtxt(generated_model / "linear_double_pendulum_results.csv", delimiter=",", skiprows=1)
     assert np.isfinite(gl).all() and np.abs(gl[:, 5:7]).max() < 1e3
+
+
+@pytest.mark.gpu
+def test_facade_threaded_and_batched(generated_model, examples, tmp_path):
+    """ModelControl's solver thread, control_at_time, update_weights, update_control_limits, BatchModelControl (C++)."""
+    exe = tmp_path / "facade_threaded"
+    lib = os.path.join(ROOT, "mahi_mpc_b200", "lib")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-pthread", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "facade_threaded.cpp"), "-o", str(exe), "-L" + lib, "-lmahi_mpc_facade",
+                    "-lmahi_mpc_b200", "-Wl,-rpath," + lib, "-ldl"], check=True)
+    r = subprocess.run([str(exe)], cwd=generated_model, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "FACADE-THREADED-OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

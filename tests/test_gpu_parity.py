@@ -454,3 +454,37 @@ def test_closed_loop_batch_vs_oracle(api, coracle, plant):
     assert np.abs(U - Uo).max() < U_ATOL and np.abs(X - Xo).max() < 1e-8
     assert np.abs(xs - x).max() < 1e-8 and np.abs(us - u).max() < U_ATOL  # final state / control written back
     assert (it[:, 1:] <= it[:, :1]).all() and (it >= 0).all()             # warm starts never need more than the cold solve
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_failed_instance_does_not_poison_the_batch(api, coracle, variant):
+    """SURVEY section 5 (failure detection): a non-finite input makes THAT instance report MMPC_SOLVE_NUMERICAL; its
+    neighbours (same warp / same CTA tile) still converge to the oracle's solution."""
+    N, B = 25, 40
+    P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B, seed_offset=9)
+    bad = [3, 17, 39]
+    x0b, trajb = x0.copy(), traj.copy()
+    x0b[3, 1] = np.nan
+    trajb[17, 5, 2] = np.inf
+    x0b[39, 0] = 1e308
+    m = api.Model("double_pendulum", N=N)
+    s = api.Solver(m, B, tol=1e-10, max_iter=50, kernel_variant=variant)
+    s.set_weights(Q, R, Rm)
+    V, lam, st = s.solve(x0b, up, trajb)
+    good = np.setdiff1d(np.arange(B), bad)
+    assert (st["status"][bad] != 0).all() and (st["status"][good] == 0).all(), st["status"]
+    Vo, _, sto, nbad = coracle.solve_batch("double_pendulum", N, P.h, False, x0[good], p[good], tol=1e-10)
+    assert nbad == 0 and np.abs(V[good] - Vo).max() < U_ATOL
+
+
+def test_max_iter_is_honoured_and_reported(api):
+    N, B = 50, 33
+    P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B)
+    m = api.Model("double_pendulum", N=N)
+    s = api.Solver(m, B, tol=1e-12, max_iter=1)
+    s.set_weights(Q, R, Rm)
+    V, lam, st = s.solve(x0, up, traj)
+    assert (st["status"] == 1).all() and (st["iterations"] == 1).all() and (st["kkt_error"] > 1e-12).all()
+    s.set_options(max_iter=200, tol=1e-5)
+    V, lam, st = s.solve(x0, up, traj)
+    assert (st["status"] == 0).all()
