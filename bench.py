@@ -93,6 +93,17 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json names the capture each figure was read from); None if there is none."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)[kernel]["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -268,7 +279,7 @@ def run_gpu(args):
         flops_per_solve = iters_mean * N * (fl_eval + fl_ric + fl_fwd) + N * sum(ops["fABH"])  # + the final convergence sweep
         fp64_peak = api.measure_fp64_peak(local)
         roofline = {"bound": "hbm", "achieved": B * bytes_per_solve / kern_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": B * bytes_per_solve / kern_s / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": B * bytes_per_solve / kern_s / 1e9 / hbm_peak, "traffic": ncu_traffic("solve_kernel_t3"), "peak_source": peak_src,
                     "kernel": "solve_kernel", "note": "the solve is FP64-pipe/latency bound, not HBM bound (SURVEY 8d): see fp64_roofline"}
         fp64 = {"bound": "fp64-dfma", "achieved": B * flops_per_solve / kern_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": B * flops_per_solve / kern_s / 1e12 / fp64_peak if fp64_peak else None,
@@ -326,7 +337,7 @@ def node_eval_bench(api, model, dev, hbm_peak):
     return {"workload": "BASELINE configs[4]: 1e7 node evaluations (g, dF/dx, dF/du dense), inputs 800 MB > L2", "nodes": n,
             "node_evals_per_s": n / t, "ms": t * 1e3,
             "roofline": {"bound": "hbm", "achieved": n * bytes_per_node / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": n * bytes_per_node / t / 1e9 / hbm_peak, "traffic": None, "bytes_per_node": bytes_per_node}}
+                         "frac": n * bytes_per_node / t / 1e9 / hbm_peak, "traffic": ncu_traffic("eval_nodes_kernel"), "bytes_per_node": bytes_per_node}}
 
 
 def latency_bench(api, dev):
