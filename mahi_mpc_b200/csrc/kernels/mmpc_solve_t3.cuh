@@ -76,10 +76,9 @@ struct T3Ctx {
 // ---- parallel phase of the backward sweep: thread (i, j) evaluates node k = k0 + j of instance i -------------
 // red slots: 0 dual_inf(max) 1 prim_inf(max) 2 theta 3 fval 4 lam_l1
 template <class M, class C>
-__device__ __noinline__ void t3_eval_node(const T3Ctx<M>& cin, int k, int i, int j, double delta, double* rec, double* red,
-                                          double* fg_tile) {
+__device__ __forceinline__ void t3_eval_node(const T3Ctx<M>& c, int k, int i, int j, double delta, double* rec, double* red,
+                                             double* fg_tile) {
     constexpr int NX = M::NX, NU = M::NU, S = C::S, NH = C::NH, I = C::I;
-    const T3Ctx<M> c = cin;
     const int N = c.N;
     const double* z = c.V + (size_t)k * S;
     double x[NX], u[NU], v[NU], r[NX], lam[NX], xn[NX], wq[NX];
@@ -283,9 +282,11 @@ struct T3Norms {
 // lane per instance) the worker warps evaluate chunk ch-1 into the other record buffer.
 // returns (valid on the serial lanes) whether every G_uu was positive definite
 template <class M, class C>
-__device__ __noinline__ bool t3_backward(const T3Ctx<M>& c, double* smem, int tid, double delta_self, T3Norms& nrm,
+__device__ __noinline__ bool t3_backward(const T3Ctx<M>& cin, double* smem, int tid, double delta_self, T3Norms& nrm_out,
                                          double* fg_tile, double* kg_tile, double* pg_tile) {
     constexpr int NX = M::NX, NU = M::NU, I = C::I;
+    const T3Ctx<M> c = cin;  // callee-local copy: the context and all accumulators stay in registers (the caller's copy has
+                             // its address taken and therefore lives in local memory)
     const int N = c.N;
     const bool worker = tid >= 32;
     const int w = tid - 32, wi = w % I, wj = w / I;
@@ -296,39 +297,39 @@ __device__ __noinline__ bool t3_backward(const T3Ctx<M>& c, double* smem, int ti
     MMPC_UNROLL for (int a = 0; a < NU * NU; ++a) V.Pvv[a] = 0.0;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) V.px[a] = 0.0;
     MMPC_UNROLL for (int a = 0; a < NU; ++a) V.pv[a] = 0.0;
-    nrm.dual_inf = nrm.prim_inf = nrm.theta = nrm.fval = nrm.lam_l1 = 0.0;
+    double n_dual = 0.0, n_prim = 0.0, n_theta = 0.0, n_fval = 0.0, n_lam = 0.0;
     bool ok = true;
     if (tid < I) dl[tid] = delta_self;
     __syncthreads();
     const double delta = worker ? dl[wi] : 0.0;
     const int nch = (N + C::CB - 1) / C::CB;
-    auto eval_chunk = [&](int ch) {
-        const int k0 = ch * C::CB, kn = min(C::CB, N - k0);
-        if (wj < kn) t3_eval_node<M, C>(c, k0 + wj, wi, wj, delta, smem + C::SM_REC + (ch & 1) * C::BUF, smem + C::SM_RED + (ch & 1) * C::REDBUF, fg_tile);
-    };
 #ifdef MMPC_T3_PROFILE
     long long t_work = 0, t_all0 = clock64();
 #endif
-    if (worker) eval_chunk(nch - 1);
-    __syncthreads();
-    for (int ch = nch - 1; ch >= 0; --ch) {
+    // step = nch: workers evaluate the last chunk (prologue); step = ch < nch: warp 0 consumes chunk ch while the workers
+    // evaluate chunk ch-1 (one call site, so the evaluator is inlined exactly once)
+    for (int step = nch; step >= 0; --step) {
 #ifdef MMPC_T3_PROFILE
         const long long t0 = clock64();
 #endif
         if (worker) {
-            if (ch > 0) eval_chunk(ch - 1);
-        } else if (tid < I) {
-            const int k0 = ch * C::CB, kn = min(C::CB, N - k0);
+            const int ch = step - 1;
+            if (ch >= 0) {
+                const int k0 = ch * C::CB, kn = min(C::CB, N - k0);
+                if (wj < kn) t3_eval_node<M, C>(c, k0 + wj, wi, wj, delta, smem + C::SM_REC + (ch & 1) * C::BUF, smem + C::SM_RED + (ch & 1) * C::REDBUF, fg_tile);
+            }
+        } else if (tid < I && step < nch) {
+            const int ch = step, k0 = ch * C::CB, kn = min(C::CB, N - k0);
             const double* rec = smem + C::SM_REC + (ch & 1) * C::BUF;
             const double* red = smem + C::SM_RED + (ch & 1) * C::REDBUF;
             for (int s = kn - 1; s >= 0; --s) {
                 const int k = k0 + s;
                 ok = t3_riccati_stage<M, C>(V, rec, s, tid, c.R, kg_tile + (size_t)k * C::KG * I + tid, pg_tile + (size_t)k * C::PG * I + tid) && ok;
-                nrm.dual_inf = fmax(nrm.dual_inf, red[(0 * C::CB + s) * I + tid]);
-                nrm.prim_inf = fmax(nrm.prim_inf, red[(1 * C::CB + s) * I + tid]);
-                nrm.theta += red[(2 * C::CB + s) * I + tid];
-                nrm.fval += red[(3 * C::CB + s) * I + tid];
-                nrm.lam_l1 += red[(4 * C::CB + s) * I + tid];
+                n_dual = fmax(n_dual, red[(0 * C::CB + s) * I + tid]);
+                n_prim = fmax(n_prim, red[(1 * C::CB + s) * I + tid]);
+                n_theta += red[(2 * C::CB + s) * I + tid];
+                n_fval += red[(3 * C::CB + s) * I + tid];
+                n_lam += red[(4 * C::CB + s) * I + tid];
             }
         }
 #ifdef MMPC_T3_PROFILE
@@ -340,6 +341,7 @@ __device__ __noinline__ bool t3_backward(const T3Ctx<M>& c, double* smem, int ti
     if (blockIdx.x == 0 && (tid == 0 || tid == 32))
         printf("[t3 backward] tid %d busy %lld of %lld cycles (%d chunks of %d)\n", tid, t_work, clock64() - t_all0, nch, C::CB);
 #endif
+    nrm_out.dual_inf = n_dual; nrm_out.prim_inf = n_prim; nrm_out.theta = n_theta; nrm_out.fval = n_fval; nrm_out.lam_l1 = n_lam;
     return ok;
 }
 
@@ -379,9 +381,11 @@ struct T3Fwd {
 // forward sweep for the tile, software pipelined: while warp 0 rolls the step through chunk ch, the worker warps stage
 // chunk ch+1's records (cp.async) and evaluate the merit terms of the full step on chunk ch-1.
 template <class M, class C>
-__device__ __noinline__ void t3_forward(const T3Ctx<M>& c, double* smem, int tid, T3Fwd& o, const double* fg_tile, const double* kg_tile,
+__device__ __noinline__ void t3_forward(const T3Ctx<M>& cin, double* smem, int tid, T3Fwd& o_out, const double* fg_tile, const double* kg_tile,
                                         const double* pg_tile) {
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
+    const T3Ctx<M> c = cin;  // register-resident copies (see t3_backward)
+    T3Fwd o;
     const int N = c.N;
     const bool worker = tid >= 32;
     const int w = tid - 32, wi = w % I, wj = w / I;
@@ -486,12 +490,14 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M>& c, double* smem, int tid
         o.th1 += red[(1 * C::CB + s) * I + tid];
     }
     __syncthreads();
+    o_out = o;
 }
 
 // merit of z + alpha_i dz for every instance of the tile (alpha per instance in shared memory)
 template <class M, class C>
-__device__ __noinline__ void t3_trial(const T3Ctx<M>& c, double* smem, int tid, double& f1, double& th1) {
+__device__ __noinline__ void t3_trial(const T3Ctx<M>& cin, double* smem, int tid, double& f1, double& th1) {
     constexpr int I = C::I;
+    const T3Ctx<M> c = cin;
     const bool worker = tid >= 32;
     const int w = tid - 32, wi = w % I, wj = w / I;
     double* red = smem + C::SM_RED;
@@ -562,6 +568,9 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_>::THREADS) solve_kernel_t3(
     }
     __syncthreads();
 
+    // plain local copies for the element-wise loops below (the struct `c` is passed by reference to the sweeps, so it lives
+    // in local memory; these do not)
+    double* const Vp = c.V; double* const LAMp = c.LAM; const double* const DVp = c.DV; const double* const LAMNp = c.LAMN;
     // per-instance solver state lives in the serial lane (tid < I) of the instance
     double nu_merit = 1.0, delta_last = 0.0, err = INFINITY, fval = 0.0;
     int it = 0, it_done = 0, status = MMPC_SOLVE_MAX_ITER, ls_total = 0, reg_total = 0;
@@ -629,13 +638,13 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_>::THREADS) solve_kernel_t3(
             constexpr int UB = 8;
             for (int e0 = NX + j; e0 < NV; e0 += C::CB * UB) {
                 double vz[UB], vd[UB];
-                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) { vz[q] = c.V[e0 + q * C::CB]; vd[q] = c.DV[e0 + q * C::CB]; }
-                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) c.V[e0 + q * C::CB] = fma(al, vd[q], vz[q]);
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) { vz[q] = Vp[e0 + q * C::CB]; vd[q] = DVp[e0 + q * C::CB]; }
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) Vp[e0 + q * C::CB] = fma(al, vd[q], vz[q]);
             }
             for (int e0 = j; e0 < Mc; e0 += C::CB * UB) {
                 double vl[UB], vn[UB];
-                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) { vl[q] = c.LAM[e0 + q * C::CB]; vn[q] = c.LAMN[e0 + q * C::CB]; }
-                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) c.LAM[e0 + q * C::CB] = fma(al, vn[q] - vl[q], vl[q]);
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) { vl[q] = LAMp[e0 + q * C::CB]; vn[q] = LAMNp[e0 + q * C::CB]; }
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) LAMp[e0 + q * C::CB] = fma(al, vn[q] - vl[q], vl[q]);
             }
         }
         __syncthreads();
@@ -646,8 +655,8 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_>::THREADS) solve_kernel_t3(
     // ---- outputs: the iterate already is the reference's V layout ----
     if (valid && worker) {
         double* Vo = io.V_out + (size_t)b * NV;
-        for (int e = j; e < NV; e += C::CB) Vo[e] = c.V[e];
-        if (io.lam_out) for (int e = j; e < Mc; e += C::CB) io.lam_out[(size_t)b * Mc + e] = c.LAM[e];
+        for (int e = j; e < NV; e += C::CB) Vo[e] = Vp[e];
+        if (io.lam_out) for (int e = j; e < Mc; e += C::CB) io.lam_out[(size_t)b * Mc + e] = LAMp[e];
     }
     if (valid && tid < I && io.stats) {
         mmpc_stats s;
@@ -681,7 +690,10 @@ struct LaunchT3 {
     static cudaError_t run(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         const int forced = io.variant >> 8;
         const int cfg = forced ? forced : 1;
-        return cfg == 2 ? go<14, 8, 4>(P, W, io, st) : go<8, 4, 4>(P, W, io, st);
+        if (cfg == 2) return go<14, 8, 4>(P, W, io, st);
+        if (cfg == 3) return go<16, 4, 4>(P, W, io, st);
+        if (cfg == 4) return go<32, 4, 4>(P, W, io, st);
+        return go<8, 4, 4>(P, W, io, st);
     }
 };
 

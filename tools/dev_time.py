@@ -1,0 +1,20 @@
+"""Developer tool: device-resident timing (CUDA events, inputs in HBM) of the batched solve for several batch sizes.
+    python -m tools.dev_time N variant B1 B2 ..."""
+import sys
+import numpy as np, torch
+import mahi_mpc_b200.api as api
+from mahi_mpc_b200 import workload
+N = int(sys.argv[1]); variant = int(sys.argv[2]); dev = torch.device("cuda", 0)
+for B in [int(v) for v in sys.argv[3:]]:
+    x0, up, traj = workload.synthetic_batch(4, 2, N, 0.002, B)
+    Q, R, Rm = workload.default_weights(4, 2)
+    m = api.Model("double_pendulum", N=N); s = api.Solver(m, B, warm_start=0, kernel_variant=variant); s.set_weights(Q, R, Rm)
+    d = [torch.from_numpy(a).to(dev) for a in (x0, up, traj)]
+    V = torch.empty(B, m.NV, dtype=torch.float64, device=dev); st = torch.empty(B, 5, dtype=torch.float64, device=dev)
+    for _ in range(3): s.solve(*d, V_out=V, stats_out=st, want_lam=False)
+    ts = []
+    for _ in range(7):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); s.solve(*d, V_out=V, stats_out=st, want_lam=False); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    ms = float(np.median(ts)); it = api.stats_from_tensor(st)["iterations"]
+    print(f"N={N} var={variant} B={B:6d} {ms:8.3f} ms  {B/ms*1e3:.3e} solves/s  iters max {it.max()} mean {it.mean():.2f}")
