@@ -89,14 +89,17 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M>& c, int k, int i, in
         lam[a] = c.LAM[(size_t)k * NX + a];
         wq[a] = 2.0 * c.Q[a];
     }
+    double lam_prev[NX], u_next[NU];  // neighbours, loaded up front so that every global load of the node is in flight together
     MMPC_UNROLL for (int a = 0; a < NU; ++a) {
         u[a] = z[NX + a];
         v[a] = k ? z[NX + a - S] : c.uinit[a];
+        u_next[a] = (k < N - 1) ? z[S + NX + a] : 0.0;
     }
+    MMPC_UNROLL for (int a = 0; a < NX; ++a) lam_prev[a] = k ? c.LAM[(size_t)(k - 1) * NX + a] : 0.0;
     double F[NX], Fx[NX * NX], Fu[NX * NU], H[NH];
     c.template step<2>(x, u, wq, r, lam, F, Fx, Fu, H);
 #define T3_REC(f) rec[((j)*C::RB + (f)) * I + i]
-#define T3_FG(f) fg_tile[((size_t)k * C::FG + (f)) * I + i]
+#define T3_FG(f, v) __stcs(&fg_tile[((size_t)k * C::FG + (f)) * I + i], (v))  // streaming: records must not evict the iterate from L2
     double qe[NX], dual = 0.0, prim = 0.0, theta = 0.0, fval = 0.0, lam1 = 0.0;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         const double e = F[a] - r[a], cr = F[a] - xn[a];
@@ -106,11 +109,11 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M>& c, int k, int i, in
         theta += fabs(cr);
         lam1 += fabs(lam[a]);
         T3_REC(C::RB_C + a) = cr;
-        T3_FG(C::FG_C + a) = cr;
+        T3_FG(C::FG_C + a, cr);
         if (k == N - 1) dual = fmax(dual, fabs(lam[a]));  // stationarity w.r.t. x_N is -lam_{N-1}
     }
-    MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) { T3_REC(C::RB_FX + a) = Fx[a]; T3_FG(C::FG_FX + a) = Fx[a]; }
-    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) { T3_REC(C::RB_FU + a) = Fu[a]; T3_FG(C::FG_FU + a) = Fu[a]; }
+    MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) { T3_REC(C::RB_FX + a) = Fx[a]; T3_FG(C::FG_FX + a, Fx[a]); }
+    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) { T3_REC(C::RB_FU + a) = Fu[a]; T3_FG(C::FG_FU + a, Fu[a]); }
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         double g = 0.0, l = 0.0;
         MMPC_UNROLL for (int q = 0; q < NX; ++q) {
@@ -118,8 +121,8 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M>& c, int k, int i, in
             l = fma(Fx[q * NX + a], lam[q], l);
         }
         T3_REC(C::RB_Q + a) = g;
-        T3_FG(C::FG_Q + a) = g;
-        if (k) dual = fmax(dual, fabs(g + l - c.LAM[(size_t)(k - 1) * NX + a]));
+        T3_FG(C::FG_Q + a, g);
+        if (k) dual = fmax(dual, fabs(g + l - lam_prev[a]));
     }
     MMPC_UNROLL for (int a = 0; a < NU; ++a) {
         double g = 0.0, l = 0.0;
@@ -129,12 +132,12 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M>& c, int k, int i, in
         }
         const double du = u[a] - v[a], dRu = 2.0 * c.R[a] * du;
         const double qu = g + dRu + 2.0 * c.Rm[a] * u[a];
-        const double dRn = (k < N - 1) ? 2.0 * c.R[a] * (z[S + NX + a] - u[a]) : 0.0;
+        const double dRn = (k < N - 1) ? 2.0 * c.R[a] * (u_next[a] - u[a]) : 0.0;
         fval = fma(c.R[a] * du, du, fval);
         fval = fma(c.Rm[a] * u[a], u[a], fval);
         dual = fmax(dual, fabs(qu + l - dRn));
-        T3_REC(C::RB_Q + NX + a) = -dRu;  T3_FG(C::FG_Q + NX + a) = -dRu;
-        T3_REC(C::RB_Q + S + a) = qu;     T3_FG(C::FG_Q + S + a) = qu;
+        T3_REC(C::RB_Q + NX + a) = -dRu;  T3_FG(C::FG_Q + NX + a, -dRu);
+        T3_REC(C::RB_Q + S + a) = qu;     T3_FG(C::FG_Q + S + a, qu);
     }
     MMPC_UNROLL for (int p = 0; p < S; ++p) MMPC_UNROLL for (int d = p; d < S; ++d) {
         double acc = H[tri(p, d, S)];
@@ -171,9 +174,9 @@ __device__ __forceinline__ bool t3_riccati_stage(T3Riccati<M>& V, const double* 
     MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) Fu[a] = T3_R(C::RB_FU + a);
     MMPC_UNROLL for (int a = 0; a < NX; ++a) cres[a] = T3_R(C::RB_C + a);
     // value function of stage k+1 -> global (the forward sweep needs it for lam_k)
-    MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) pg[(C::PG_XX + a) * I] = V.Pxx[a];
-    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) pg[(C::PG_XV + a) * I] = V.Pxv[a];
-    MMPC_UNROLL for (int a = 0; a < NX; ++a) pg[(C::PG_X + a) * I] = V.px[a];
+    MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) __stcs(&pg[(C::PG_XX + a) * I], V.Pxx[a]);
+    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) __stcs(&pg[(C::PG_XV + a) * I], V.Pxv[a]);
+    MMPC_UNROLL for (int a = 0; a < NX; ++a) __stcs(&pg[(C::PG_X + a) * I], V.px[a]);
     double y[NX], yv[NU];
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         double t = V.px[a];
@@ -245,9 +248,9 @@ __device__ __forceinline__ bool t3_riccati_stage(T3Riccati<M>& V, const double* 
     }
     MMPC_UNROLL for (int b = 0; b < NU; ++b) k0[b] = -gu[b];
     chol_solve<NU>(Guu, k0);
-    MMPC_UNROLL for (int a = 0; a < NU * NX; ++a) kg[(C::KG_KX + a) * I] = Kx[a];
-    MMPC_UNROLL for (int a = 0; a < NU * NU; ++a) kg[(C::KG_KV + a) * I] = Kv[a];
-    MMPC_UNROLL for (int a = 0; a < NU; ++a) kg[(C::KG_K0 + a) * I] = k0[a];
+    MMPC_UNROLL for (int a = 0; a < NU * NX; ++a) __stcs(&kg[(C::KG_KX + a) * I], Kx[a]);
+    MMPC_UNROLL for (int a = 0; a < NU * NU; ++a) __stcs(&kg[(C::KG_KV + a) * I], Kv[a]);
+    MMPC_UNROLL for (int a = 0; a < NU; ++a) __stcs(&kg[(C::KG_K0 + a) * I], k0[a]);
     const double qv0 = 0.0;
     (void)qv0;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
