@@ -658,8 +658,17 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_>::THREADS) solve_kernel_t3(
     // ---- outputs: the iterate already is the reference's V layout ----
     if (valid && worker) {
         double* Vo = io.V_out + (size_t)b * NV;
-        for (int e = j; e < NV; e += C::CB) Vo[e] = Vp[e];
-        if (io.lam_out) for (int e = j; e < Mc; e += C::CB) io.lam_out[(size_t)b * Mc + e] = LAMp[e];
+        constexpr int UB = 8;  // batched so that the loads of one batch are in flight together
+        for (int e0 = j; e0 < NV; e0 += C::CB * UB) {
+            double t[UB];
+            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) t[q] = Vp[e0 + q * C::CB];
+            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) __stcs(&Vo[e0 + q * C::CB], t[q]);
+        }
+        if (io.lam_out) for (int e0 = j; e0 < Mc; e0 += C::CB * UB) {
+            double t[UB];
+            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) t[q] = LAMp[e0 + q * C::CB];
+            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) __stcs(&io.lam_out[(size_t)b * Mc + e0 + q * C::CB], t[q]);
+        }
     }
     if (valid && tid < I && io.stats) {
         mmpc_stats s;
