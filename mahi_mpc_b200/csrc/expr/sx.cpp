@@ -499,7 +499,7 @@ std::string emit_body(const std::vector<EmitInput>& ins, const std::vector<EmitO
         const std::string v = "v" + std::to_string(id);
         if ((n.op == Op::Sin || n.op == Op::Cos) && sin_of.count(n.a) && cos_of.count(n.a)) {
             const int sid = sin_of[n.a], cid = cos_of[n.a];
-            os << ind << "double v" << sid << ", v" << cid << "; sincos(" << ref(n.a) << ", &v" << sid << ", &v" << cid << ");\n";
+            os << ind << "double v" << sid << ", v" << cid << "; " << (cuda ? "MMPC_SINCOS(" : "sincos(") << ref(n.a) << ", &v" << sid << ", &v" << cid << ");\n";
             nm[sid] = "v" + std::to_string(sid);
             nm[cid] = "v" + std::to_string(cid);
             done[sid] = done[cid] = true;
@@ -533,7 +533,6 @@ std::string emit_body(const std::vector<EmitInput>& ins, const std::vector<EmitO
             if (o.skip_zero && g.is_zero(o.ids[i])) continue;
             os << ind << o.cname << "[" << i << "] = " << ref(o.ids[i]) << ";\n";
         }
-    (void)cuda;
     return os.str();
 }
 
