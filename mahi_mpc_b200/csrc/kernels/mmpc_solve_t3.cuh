@@ -51,6 +51,13 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
 }
 
+// Structural sparsity of the one-step Jacobians under Euler / linearised steps: Fx = I + h A and Fu = h B inherit the
+// pattern of A and B (e.g. the kinematic rows q' = qdot), which the generator reports as bit masks.  In the fully unrolled
+// loops below the guards fold at compile time, so structurally zero products are never issued (CasADi's generated code
+// exploits the same sparsity).  Not valid for RK4 (fill-in); T3 is Euler/linearised only.
+#define T3_FXNZ(r, c) (((r) == (c)) || ((M::A_MASK >> ((r) * NX + (c))) & 1ULL))
+#define T3_FUNZ(r, c) ((M::B_MASK >> ((r) * NU + (c))) & 1ULL)
+
 template <class M>
 struct T3Ctx {
     static constexpr int NX = M::NX, NU = M::NU, S = NX + NU;
@@ -112,11 +119,11 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M>& c, int k, int i, in
         T3_FG(C::FG_C + a, cr);
         if (k == N - 1) dual = fmax(dual, fabs(lam[a]));  // stationarity w.r.t. x_N is -lam_{N-1}
     }
-    MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) { T3_REC(C::RB_FX + a) = Fx[a]; T3_FG(C::FG_FX + a, Fx[a]); }
-    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) { T3_REC(C::RB_FU + a) = Fu[a]; T3_FG(C::FG_FU + a, Fu[a]); }
+    MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) if (T3_FXNZ(a / NX, a % NX)) { T3_REC(C::RB_FX + a) = Fx[a]; T3_FG(C::FG_FX + a, Fx[a]); }
+    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) if (T3_FUNZ(a / NU, a % NU)) { T3_REC(C::RB_FU + a) = Fu[a]; T3_FG(C::FG_FU + a, Fu[a]); }
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         double g = 0.0, l = 0.0;
-        MMPC_UNROLL for (int q = 0; q < NX; ++q) {
+        MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FXNZ(q, a)) {
             g = fma(Fx[q * NX + a], qe[q], g);
             l = fma(Fx[q * NX + a], lam[q], l);
         }
@@ -126,7 +133,7 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M>& c, int k, int i, in
     }
     MMPC_UNROLL for (int a = 0; a < NU; ++a) {
         double g = 0.0, l = 0.0;
-        MMPC_UNROLL for (int q = 0; q < NX; ++q) {
+        MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FUNZ(q, a)) {
             g = fma(Fu[q * NU + a], qe[q], g);
             l = fma(Fu[q * NU + a], lam[q], l);
         }
@@ -142,9 +149,12 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M>& c, int k, int i, in
     MMPC_UNROLL for (int p = 0; p < S; ++p) MMPC_UNROLL for (int d = p; d < S; ++d) {
         double acc = H[tri(p, d, S)];
         MMPC_UNROLL for (int q = 0; q < NX; ++q) {
-            const double fa = p < NX ? Fx[q * NX + p] : Fu[q * NU + p - NX];
-            const double fd = d < NX ? Fx[q * NX + d] : Fu[q * NU + d - NX];
-            acc = fma(wq[q] * fa, fd, acc);
+            const bool nzp = p < NX ? T3_FXNZ(q, p) : T3_FUNZ(q, p - NX), nzd = d < NX ? T3_FXNZ(q, d) : T3_FUNZ(q, d - NX);
+            if (nzp && nzd) {
+                const double fa = p < NX ? Fx[q * NX + p] : Fu[q * NU + p - NX];
+                const double fd = d < NX ? Fx[q * NX + d] : Fu[q * NU + d - NX];
+                acc = fma(wq[q] * fa, fd, acc);
+            }
         }
         if (p == d) acc += delta + (p >= NX ? 2.0 * (c.R[p - NX] + c.Rm[p - NX]) : 0.0);
         T3_REC(C::RB_H + tri(p, d, S)) = acc;
@@ -170,8 +180,8 @@ __device__ __forceinline__ bool t3_riccati_stage(T3Riccati<M>& V, const double* 
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
 #define T3_R(f) rec[((s)*C::RB + (f)) * I + i]
     double Fx[NX * NX], Fu[NX * NU], cres[NX];
-    MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) Fx[a] = T3_R(C::RB_FX + a);
-    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) Fu[a] = T3_R(C::RB_FU + a);
+    MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) Fx[a] = T3_FXNZ(a / NX, a % NX) ? T3_R(C::RB_FX + a) : 0.0;
+    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) Fu[a] = T3_FUNZ(a / NU, a % NU) ? T3_R(C::RB_FU + a) : 0.0;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) cres[a] = T3_R(C::RB_C + a);
     // value function of stage k+1 -> global (the forward sweep needs it for lam_k)
     MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) __stcs(&pg[(C::PG_XX + a) * I], V.Pxx[a]);
@@ -192,12 +202,12 @@ __device__ __forceinline__ bool t3_riccati_stage(T3Riccati<M>& V, const double* 
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         MMPC_UNROLL for (int b = 0; b < NX; ++b) {
             double t = 0.0;
-            MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(V.Pxx[a * NX + q], Fx[q * NX + b], t);
+            MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FXNZ(q, b)) t = fma(V.Pxx[a * NX + q], Fx[q * NX + b], t);
             PA[a * NX + b] = t;
         }
         MMPC_UNROLL for (int b = 0; b < NU; ++b) {
             double t = V.Pxv[a * NU + b];
-            MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(V.Pxx[a * NX + q], Fu[q * NU + b], t);
+            MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FUNZ(q, b)) t = fma(V.Pxx[a * NX + q], Fu[q * NU + b], t);
             PB[a * NU + b] = t;
         }
     }
@@ -205,31 +215,31 @@ __device__ __forceinline__ bool t3_riccati_stage(T3Riccati<M>& V, const double* 
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         MMPC_UNROLL for (int b = a; b < NX; ++b) {
             double t = T3_R(C::RB_H + tri(a, b, S));
-            MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(Fx[q * NX + a], PA[q * NX + b], t);
+            MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FXNZ(q, a)) t = fma(Fx[q * NX + a], PA[q * NX + b], t);
             Gxx[a * NX + b] = t;
             Gxx[b * NX + a] = t;
         }
         MMPC_UNROLL for (int b = 0; b < NU; ++b) {
             double t = T3_R(C::RB_H + tri(a, NX + b, S));
-            MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(Fx[q * NX + a], PB[q * NU + b], t);
+            MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FXNZ(q, a)) t = fma(Fx[q * NX + a], PB[q * NU + b], t);
             Gxu[a * NU + b] = t;
         }
         double t = T3_R(C::RB_Q + a);
-        MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(Fx[q * NX + a], y[q], t);
+        MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FXNZ(q, a)) t = fma(Fx[q * NX + a], y[q], t);
         gx[a] = t;
     }
     MMPC_UNROLL for (int a = 0; a < NU; ++a) {
         MMPC_UNROLL for (int b = a; b < NU; ++b) {
             double t = T3_R(C::RB_H + tri(NX + a, NX + b, S)) + 0.5 * (V.Pvv[a * NU + b] + V.Pvv[b * NU + a]);
             MMPC_UNROLL for (int q = 0; q < NX; ++q) {
-                t = fma(Fu[q * NU + a], PB[q * NU + b], t);
-                t = fma(V.Pxv[q * NU + a], Fu[q * NU + b], t);
+                if (T3_FUNZ(q, a)) t = fma(Fu[q * NU + a], PB[q * NU + b], t);
+                if (T3_FUNZ(q, b)) t = fma(V.Pxv[q * NU + a], Fu[q * NU + b], t);
             }
             Guu[a * NU + b] = t;
             Guu[b * NU + a] = t;
         }
         double t = T3_R(C::RB_Q + S + a) + yv[a];
-        MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(Fu[q * NU + a], y[q], t);
+        MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FUNZ(q, a)) t = fma(Fu[q * NU + a], y[q], t);
         gu[a] = t;
     }
     const bool ok = chol<NU>(Guu);
@@ -448,8 +458,8 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M>& cin, double* smem, int t
                 }
                 MMPC_UNROLL for (int a = 0; a < NX; ++a) {
                     double t = T3_F(C::FG_C + a);
-                    MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(T3_F(C::FG_FX + a * NX + q), dx[q], t);
-                    MMPC_UNROLL for (int q = 0; q < NU; ++q) t = fma(T3_F(C::FG_FU + a * NU + q), du[q], t);
+                    MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FXNZ(a, q)) t = fma(T3_F(C::FG_FX + a * NX + q), dx[q], t);
+                    MMPC_UNROLL for (int q = 0; q < NU; ++q) if (T3_FUNZ(a, q)) t = fma(T3_F(C::FG_FU + a * NU + q), du[q], t);
                     dxn[a] = t;
                 }
                 // directional derivative of the objective: q~ . (dx, dv, du)
