@@ -30,12 +30,29 @@ struct T3 {
     static constexpr int CF = CF_;  // nodes per chunk in the forward sweep (CF <= CB)
     static constexpr int WORKERS = I * CB;
     static constexpr int THREADS = 32 + WORKERS;
+    // Fx and Fu are stored compacted to their structural non-zeros (generator masks; dense if a mask does not fit 64 bits);
+    // the value-function block Pxx is stored as its upper triangle
+    static constexpr bool SPARSE = NX * NX <= 64 && NX * NU <= 64;
+    static constexpr unsigned long long fx_mask() {
+        unsigned long long m = SPARSE ? M::A_MASK : ~0ULL;
+        if (SPARSE) for (int i = 0; i < NX; ++i) m |= 1ULL << (i * NX + i);
+        return m;
+    }
+    static constexpr unsigned long long fu_mask() { return SPARSE ? M::B_MASK : ~0ULL; }
+    static constexpr int popc(unsigned long long m, int nbits) {
+        int c = 0;
+        for (int i = 0; i < nbits && i < 64; ++i) c += (int)((m >> i) & 1ULL);
+        return c;
+    }
+    static constexpr unsigned long long FXM = fx_mask(), FUM = fu_mask();
+    static constexpr int NFX = SPARSE ? popc(FXM, NX * NX) : NX * NX, NFU = SPARSE ? popc(FUM, NX * NU) : NX * NU;
+    static constexpr int NPX = NX * (NX + 1) / 2;
     // backward record fields (shared): Fx | Fu | H (packed full stage Hessian) | c | q~ = (qx, qv, qu)
-    static constexpr int RB_FX = 0, RB_FU = RB_FX + NX * NX, RB_H = RB_FU + NX * NU, RB_C = RB_H + NH, RB_Q = RB_C + NX, RB = RB_Q + N2;
+    static constexpr int RB_FX = 0, RB_FU = RB_FX + NFX, RB_H = RB_FU + NFU, RB_C = RB_H + NH, RB_Q = RB_C + NX, RB = RB_Q + N2;
     // global tile records per node
-    static constexpr int FG_FX = 0, FG_FU = NX * NX, FG_C = FG_FU + NX * NU, FG_Q = FG_C + NX, FG = FG_Q + N2;
+    static constexpr int FG_FX = 0, FG_FU = NFX, FG_C = FG_FU + NFU, FG_Q = FG_C + NX, FG = FG_Q + N2;
     static constexpr int KG_KX = 0, KG_KV = NU * NX, KG_K0 = KG_KV + NU * NU, KG = KG_K0 + NU;
-    static constexpr int PG_XX = 0, PG_XV = NX * NX, PG_X = PG_XV + NX * NU, PG = PG_X + NX;
+    static constexpr int PG_XX = 0, PG_XV = NPX, PG_X = PG_XV + NX * NU, PG = PG_X + NX;
     // forward record (shared) = FG | KG | PG
     static constexpr int RF_K = FG, RF_P = FG + KG, RF = FG + KG + PG;
     static constexpr int BUF = (CB * RB > CF * RF ? CB * RB : CF * RF) * I;  // one record buffer (two are used)
@@ -57,6 +74,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 // exploits the same sparsity).  Not valid for RK4 (fill-in); T3 is Euler/linearised only.
 #define T3_FXNZ(r, c) (((r) == (c)) || ((M::A_MASK >> ((r) * NX + (c))) & 1ULL))
 #define T3_FUNZ(r, c) ((M::B_MASK >> ((r) * NU + (c))) & 1ULL)
+// slot of flat entry a in the compacted storage (folds to a constant in the unrolled loops)
+#define T3_FXSLOT(a) (C::SPARSE ? __popcll(C::FXM & ((1ULL << (a)) - 1ULL)) : (a))
+#define T3_FUSLOT(a) (C::SPARSE ? __popcll(C::FUM & ((1ULL << (a)) - 1ULL)) : (a))
 
 template <class M>
 struct T3Ctx {
@@ -119,8 +139,8 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M>& c, int k, int i, in
         T3_FG(C::FG_C + a, cr);
         if (k == N - 1) dual = fmax(dual, fabs(lam[a]));  // stationarity w.r.t. x_N is -lam_{N-1}
     }
-    MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) if (T3_FXNZ(a / NX, a % NX)) { T3_REC(C::RB_FX + a) = Fx[a]; T3_FG(C::FG_FX + a, Fx[a]); }
-    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) if (T3_FUNZ(a / NU, a % NU)) { T3_REC(C::RB_FU + a) = Fu[a]; T3_FG(C::FG_FU + a, Fu[a]); }
+    MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) if (T3_FXNZ(a / NX, a % NX)) { T3_REC(C::RB_FX + T3_FXSLOT(a)) = Fx[a]; T3_FG(C::FG_FX + T3_FXSLOT(a), Fx[a]); }
+    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) if (T3_FUNZ(a / NU, a % NU)) { T3_REC(C::RB_FU + T3_FUSLOT(a)) = Fu[a]; T3_FG(C::FG_FU + T3_FUSLOT(a), Fu[a]); }
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         double g = 0.0, l = 0.0;
         MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FXNZ(q, a)) {
@@ -180,11 +200,11 @@ __device__ __forceinline__ bool t3_riccati_stage(T3Riccati<M>& V, const double* 
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
 #define T3_R(f) rec[((s)*C::RB + (f)) * I + i]
     double Fx[NX * NX], Fu[NX * NU], cres[NX];
-    MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) Fx[a] = T3_FXNZ(a / NX, a % NX) ? T3_R(C::RB_FX + a) : 0.0;
-    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) Fu[a] = T3_FUNZ(a / NU, a % NU) ? T3_R(C::RB_FU + a) : 0.0;
+    MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) Fx[a] = T3_FXNZ(a / NX, a % NX) ? T3_R(C::RB_FX + T3_FXSLOT(a)) : 0.0;
+    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) Fu[a] = T3_FUNZ(a / NU, a % NU) ? T3_R(C::RB_FU + T3_FUSLOT(a)) : 0.0;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) cres[a] = T3_R(C::RB_C + a);
     // value function of stage k+1 -> global (the forward sweep needs it for lam_k)
-    MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) __stcs(&pg[(C::PG_XX + a) * I], V.Pxx[a]);
+    MMPC_UNROLL for (int a = 0; a < NX; ++a) MMPC_UNROLL for (int b = a; b < NX; ++b) __stcs(&pg[(C::PG_XX + tri(a, b, NX)) * I], V.Pxx[a * NX + b]);
     MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) __stcs(&pg[(C::PG_XV + a) * I], V.Pxv[a]);
     MMPC_UNROLL for (int a = 0; a < NX; ++a) __stcs(&pg[(C::PG_X + a) * I], V.px[a]);
     double y[NX], yv[NU];
@@ -458,8 +478,8 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M>& cin, double* smem, int t
                 }
                 MMPC_UNROLL for (int a = 0; a < NX; ++a) {
                     double t = T3_F(C::FG_C + a);
-                    MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FXNZ(a, q)) t = fma(T3_F(C::FG_FX + a * NX + q), dx[q], t);
-                    MMPC_UNROLL for (int q = 0; q < NU; ++q) if (T3_FUNZ(a, q)) t = fma(T3_F(C::FG_FU + a * NU + q), du[q], t);
+                    MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FXNZ(a, q)) t = fma(T3_F(C::FG_FX + T3_FXSLOT(a * NX + q)), dx[q], t);
+                    MMPC_UNROLL for (int q = 0; q < NU; ++q) if (T3_FUNZ(a, q)) t = fma(T3_F(C::FG_FU + T3_FUSLOT(a * NU + q)), du[q], t);
                     dxn[a] = t;
                 }
                 // directional derivative of the objective: q~ . (dx, dv, du)
@@ -470,7 +490,7 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M>& cin, double* smem, int t
                 }
                 MMPC_UNROLL for (int a = 0; a < NX; ++a) {
                     double t = T3_F(C::RF_P + C::PG_X + a);
-                    MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(T3_F(C::RF_P + C::PG_XX + a * NX + q), dxn[q], t);
+                    MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(T3_F(C::RF_P + C::PG_XX + trisym(a, q, NX)), dxn[q], t);
                     MMPC_UNROLL for (int q = 0; q < NU; ++q) t = fma(T3_F(C::RF_P + C::PG_XV + a * NU + q), du[q], t);
                     c.LAMN[(size_t)k * NX + a] = t;
                     o.lam_inf = fmax(o.lam_inf, fabs(t));
