@@ -78,12 +78,13 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 #define T3_FXSLOT(a) (C::SPARSE ? __popcll(C::FXM & ((1ULL << (a)) - 1ULL)) : (a))
 #define T3_FUSLOT(a) (C::SPARSE ? __popcll(C::FUM & ((1ULL << (a)) - 1ULL)) : (a))
 
-template <class M>
+template <class M, int I_>
 struct T3Ctx {
-    static constexpr int NX = M::NX, NU = M::NU, S = NX + NU;
+    static constexpr int NX = M::NX, NU = M::NU, S = NX + NU, I = I_;
     const mmpc_problem& P;
     int N;
-    double *V, *LAM, *DV, *LAMN, *LINp;  // this thread's instance (AoS)
+    double *V, *LAM, *DV, *LAMN;  // this thread's instance inside the tile arrays: element e lives at [e * I]
+    double* LINp;                 // linearisation data of the instance (AoS)
     const double* traj;
     double Q[NX], R[NU], Rm[NU], uinit[NU];
     __device__ T3Ctx(const mmpc_problem& P_) : P(P_) {}
@@ -92,7 +93,7 @@ struct T3Ctx {
                                          double* F, double* Fx, double* Fu, double* Hs) const {
         if (P.is_linear) {
             double x0[NX];
-            MMPC_UNROLL for (int i = 0; i < NX; ++i) x0[i] = V[i];
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) x0[i] = V[(size_t)i * I];
             step_linear<M, WANT>(P.h, x, u, LINp, LINp + NX * NX, LINp + NX * NX + NX * NU, x0, uinit, F, Fx, Fu, Hs);
         } else {
             step_euler<M, WANT>(P.h, x, u, wq, r, lam, F, Fx, Fu, Hs);
@@ -100,33 +101,47 @@ struct T3Ctx {
     }
 };
 
+// L2 -> L1 prefetch of the iterate rows node k's evaluation reads (issued one chunk ahead: the evaluation otherwise
+// starts with a dependent chain of L2 round trips)
+__device__ __forceinline__ void t3_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <class M, class C>
+__device__ __forceinline__ void t3_prefetch_node(const T3Ctx<M, C::I>& c, int k) {
+    constexpr int NX = M::NX, S = C::S, I = C::I;
+    const double* z = c.V + (size_t)k * S * I;
+    MMPC_UNROLL for (int a = 0; a < S + NX; ++a) t3_prefetch(z + a * I);  // x_k, u_k, x_{k+1}; u_{k-1} and u_{k+1} belong to the neighbours
+    MMPC_UNROLL for (int a = 0; a < NX; ++a) t3_prefetch(c.LAM + ((size_t)k * NX + a) * I);
+    t3_prefetch(c.traj + (size_t)k * NX);
+}
+
 // ---- parallel phase of the backward sweep: thread (i, j) evaluates node k = k0 + j of instance i -------------
 // red slots: 0 dual_inf(max) 1 prim_inf(max) 2 theta 3 fval 4 lam_l1
 template <class M, class C>
-__device__ __forceinline__ void t3_eval_node(const T3Ctx<M>& c, int k, int i, int j, double delta, double* rec, double* red,
+__device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I>& c, int k, int i, int j, double delta, double* rec, double* red,
                                              double* fg_tile) {
     constexpr int NX = M::NX, NU = M::NU, S = C::S, NH = C::NH, I = C::I;
     const int N = c.N;
-    const double* z = c.V + (size_t)k * S;
+    const double* z = c.V + (size_t)k * S * I;
     double x[NX], u[NU], v[NU], r[NX], lam[NX], xn[NX], wq[NX];
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
-        x[a] = z[a];
-        xn[a] = z[S + a];
+        x[a] = z[a * I];
+        xn[a] = z[(S + a) * I];
         r[a] = c.traj[(size_t)k * NX + a];
-        lam[a] = c.LAM[(size_t)k * NX + a];
+        lam[a] = c.LAM[((size_t)k * NX + a) * I];
         wq[a] = 2.0 * c.Q[a];
     }
     double lam_prev[NX], u_next[NU];  // neighbours, loaded up front so that every global load of the node is in flight together
     MMPC_UNROLL for (int a = 0; a < NU; ++a) {
-        u[a] = z[NX + a];
-        v[a] = k ? z[NX + a - S] : c.uinit[a];
-        u_next[a] = (k < N - 1) ? z[S + NX + a] : 0.0;
+        u[a] = z[(NX + a) * I];
+        v[a] = k ? z[(NX + a - S) * I] : c.uinit[a];
+        u_next[a] = (k < N - 1) ? z[(S + NX + a) * I] : 0.0;
     }
-    MMPC_UNROLL for (int a = 0; a < NX; ++a) lam_prev[a] = k ? c.LAM[(size_t)(k - 1) * NX + a] : 0.0;
+    MMPC_UNROLL for (int a = 0; a < NX; ++a) lam_prev[a] = k ? c.LAM[((size_t)(k - 1) * NX + a) * I] : 0.0;
     double F[NX], Fx[NX * NX], Fu[NX * NU], H[NH];
     c.template step<2>(x, u, wq, r, lam, F, Fx, Fu, H);
-#define T3_REC(f) rec[((j)*C::RB + (f)) * I + i]
-#define T3_FG(f, v) __stcs(&fg_tile[((size_t)k * C::FG + (f)) * I + i], (v))  // streaming: records must not evict the iterate from L2
+    double* const recp = rec + (size_t)j * C::RB * I + i;
+    double* const fgp = fg_tile + (size_t)k * C::FG * I + i;
+#define T3_REC(f) recp[(f) * I]
+#define T3_FG(f, v) __stcs(&fgp[(f) * I], (v))  // streaming: records must not evict the iterate from L2
     double qe[NX], dual = 0.0, prim = 0.0, theta = 0.0, fval = 0.0, lam1 = 0.0;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         const double e = F[a] - r[a], cr = F[a] - xn[a];
@@ -198,7 +213,8 @@ struct T3Riccati {
 template <class M, class C>
 __device__ __forceinline__ bool t3_riccati_stage(T3Riccati<M>& V, const double* rec, int s, int i, const double* R, double* kg, double* pg) {
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
-#define T3_R(f) rec[((s)*C::RB + (f)) * I + i]
+    const double* const recp = rec + (size_t)s * C::RB * I + i;
+#define T3_R(f) recp[(f) * I]
     double Fx[NX * NX], Fu[NX * NU], cres[NX];
     MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) Fx[a] = T3_FXNZ(a / NX, a % NX) ? T3_R(C::RB_FX + T3_FXSLOT(a)) : 0.0;
     MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) Fu[a] = T3_FUNZ(a / NU, a % NU) ? T3_R(C::RB_FU + T3_FUSLOT(a)) : 0.0;
@@ -315,10 +331,10 @@ struct T3Norms {
 // lane per instance) the worker warps evaluate chunk ch-1 into the other record buffer.
 // returns (valid on the serial lanes) whether every G_uu was positive definite
 template <class M, class C>
-__device__ __noinline__ bool t3_backward(const T3Ctx<M>& cin, double* smem, int tid, double delta_self, T3Norms& nrm_out,
+__device__ __noinline__ bool t3_backward(const T3Ctx<M, C::I>& cin, double* smem, int tid, double delta_self, T3Norms& nrm_out,
                                          double* fg_tile, double* kg_tile, double* pg_tile) {
     constexpr int NX = M::NX, NU = M::NU, I = C::I;
-    const T3Ctx<M> c = cin;  // callee-local copy: the context and all accumulators stay in registers (the caller's copy has
+    const T3Ctx<M, C::I> c = cin;  // callee-local copy: the context and all accumulators stay in registers (the caller's copy has
                              // its address taken and therefore lives in local memory)
     const int N = c.N;
     const bool worker = tid >= 32;
@@ -348,11 +364,12 @@ __device__ __noinline__ bool t3_backward(const T3Ctx<M>& cin, double* smem, int 
         if (worker) {
             const int ch = step - 1;
             if (ch >= 0) {
-                const int k0 = ch * C::CB, kn = min(C::CB, N - k0);
+                const int k0 = (int)((long long)ch * N / nch), kn = (int)((long long)(ch + 1) * N / nch) - k0;  // balanced chunks (<= CB nodes)
+                if (ch > 0 && wj < k0 - (int)((long long)(ch - 1) * N / nch)) t3_prefetch_node<M, C>(c, (int)((long long)(ch - 1) * N / nch) + wj);
                 if (wj < kn) t3_eval_node<M, C>(c, k0 + wj, wi, wj, delta, smem + C::SM_REC + (ch & 1) * C::BUF, smem + C::SM_RED + (ch & 1) * C::REDBUF, fg_tile);
             }
         } else if (tid < I && step < nch) {
-            const int ch = step, k0 = ch * C::CB, kn = min(C::CB, N - k0);
+            const int ch = step, k0 = (int)((long long)ch * N / nch), kn = (int)((long long)(ch + 1) * N / nch) - k0;
             const double* rec = smem + C::SM_REC + (ch & 1) * C::BUF;
             const double* red = smem + C::SM_RED + (ch & 1) * C::REDBUF;
             for (int s = kn - 1; s >= 0; --s) {
@@ -379,19 +396,19 @@ __device__ __noinline__ bool t3_backward(const T3Ctx<M>& cin, double* smem, int 
 }
 
 // merit pieces of node k at z + alpha dz
-template <class M>
-__device__ __forceinline__ void t3_trial_node(const T3Ctx<M>& c, int k, double alpha, double& f1, double& th1) {
+template <class M, int I>
+__device__ __forceinline__ void t3_trial_node(const T3Ctx<M, I>& c, int k, double alpha, double& f1, double& th1) {
     constexpr int NX = M::NX, NU = M::NU, S = NX + NU;
-    const double* z = c.V + (size_t)k * S;
-    const double* d = c.DV + (size_t)k * S;
+    const double* z = c.V + (size_t)k * S * I;
+    const double* d = c.DV + (size_t)k * S * I;
     double x[NX], u[NU], v[NU], xn[NX], F[NX];
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
-        x[a] = fma(alpha, d[a], z[a]);
-        xn[a] = fma(alpha, d[S + a], z[S + a]);
+        x[a] = fma(alpha, d[a * I], z[a * I]);
+        xn[a] = fma(alpha, d[(S + a) * I], z[(S + a) * I]);
     }
     MMPC_UNROLL for (int a = 0; a < NU; ++a) {
-        u[a] = fma(alpha, d[NX + a], z[NX + a]);
-        v[a] = k ? fma(alpha, d[NX + a - S], z[NX + a - S]) : c.uinit[a];
+        u[a] = fma(alpha, d[(NX + a) * I], z[(NX + a) * I]);
+        v[a] = k ? fma(alpha, d[(NX + a - S) * I], z[(NX + a - S) * I]) : c.uinit[a];
     }
     c.template step<0>(x, u, nullptr, nullptr, nullptr, F, nullptr, nullptr, nullptr);
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
@@ -414,10 +431,10 @@ struct T3Fwd {
 // forward sweep for the tile, software pipelined: while warp 0 rolls the step through chunk ch, the worker warps stage
 // chunk ch+1's records (cp.async) and evaluate the merit terms of the full step on chunk ch-1.
 template <class M, class C>
-__device__ __noinline__ void t3_forward(const T3Ctx<M>& cin, double* smem, int tid, T3Fwd& o_out, const double* fg_tile, const double* kg_tile,
+__device__ __noinline__ void t3_forward(const T3Ctx<M, C::I>& cin, double* smem, int tid, T3Fwd& o_out, const double* fg_tile, const double* kg_tile,
                                         const double* pg_tile) {
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
-    const T3Ctx<M> c = cin;  // register-resident copies (see t3_backward)
+    const T3Ctx<M, C::I> c = cin;  // register-resident copies (see t3_backward)
     T3Fwd o;
     const int N = c.N;
     const bool worker = tid >= 32;
@@ -445,7 +462,7 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M>& cin, double* smem, int t
     double f1 = 0.0, th1 = 0.0;  // worker-local merit sums
     auto trial_chunk = [&](int ch) {  // workers with node slot < CF take part
         const int k0 = ch * C::CF, kn = min(C::CF, N - k0);
-        if (wj < kn) t3_trial_node<M>(c, k0 + wj, 1.0, f1, th1);
+        if (wj < kn) t3_trial_node<M, I>(c, k0 + wj, 1.0, f1, th1);
     };
 #ifdef MMPC_T3_PROFILE
     long long t_work = 0, t_all0 = clock64();
@@ -468,7 +485,8 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M>& cin, double* smem, int t
             const double* rec = smem + C::SM_REC + (ch & 1) * C::BUF;
             for (int s = 0; s < kn; ++s) {
                 const int k = k0 + s;
-#define T3_F(f) rec[((s)*C::RF + (f)) * I + tid]
+                const double* const recp = rec + (size_t)s * C::RF * I + tid;
+#define T3_F(f) recp[(f) * I]
                 double du[NU], dxn[NX];
                 MMPC_UNROLL for (int a = 0; a < NU; ++a) {
                     double t = T3_F(C::RF_K + C::KG_K0 + a);
@@ -492,13 +510,13 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M>& cin, double* smem, int t
                     double t = T3_F(C::RF_P + C::PG_X + a);
                     MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(T3_F(C::RF_P + C::PG_XX + trisym(a, q, NX)), dxn[q], t);
                     MMPC_UNROLL for (int q = 0; q < NU; ++q) t = fma(T3_F(C::RF_P + C::PG_XV + a * NU + q), du[q], t);
-                    c.LAMN[(size_t)k * NX + a] = t;
+                    c.LAMN[((size_t)k * NX + a) * I] = t;
                     o.lam_inf = fmax(o.lam_inf, fabs(t));
                     o.finite = o.finite && isfinite(t) && isfinite(dxn[a]);
                 }
 #undef T3_F
-                MMPC_UNROLL for (int a = 0; a < NU; ++a) c.DV[(size_t)k * S + NX + a] = du[a];
-                MMPC_UNROLL for (int a = 0; a < NX; ++a) c.DV[(size_t)(k + 1) * S + a] = dxn[a];
+                MMPC_UNROLL for (int a = 0; a < NU; ++a) c.DV[((size_t)k * S + NX + a) * I] = du[a];
+                MMPC_UNROLL for (int a = 0; a < NX; ++a) c.DV[((size_t)(k + 1) * S + a) * I] = dxn[a];
                 MMPC_UNROLL for (int a = 0; a < NX; ++a) dx[a] = dxn[a];
                 MMPC_UNROLL for (int a = 0; a < NU; ++a) dv[a] = du[a];
             }
@@ -528,16 +546,16 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M>& cin, double* smem, int t
 
 // merit of z + alpha_i dz for every instance of the tile (alpha per instance in shared memory)
 template <class M, class C>
-__device__ __noinline__ void t3_trial(const T3Ctx<M>& cin, double* smem, int tid, double& f1, double& th1) {
+__device__ __noinline__ void t3_trial(const T3Ctx<M, C::I>& cin, double* smem, int tid, double& f1, double& th1) {
     constexpr int I = C::I;
-    const T3Ctx<M> c = cin;
+    const T3Ctx<M, C::I> c = cin;
     const bool worker = tid >= 32;
     const int w = tid - 32, wi = w % I, wj = w / I;
     double* red = smem + C::SM_RED;
     if (worker) {
         const double alpha = smem[C::SM_INST + I + wi];
         double a1 = 0.0, a2 = 0.0;
-        for (int k = wj; k < c.N; k += C::CB) t3_trial_node<M>(c, k, alpha, a1, a2);
+        for (int k = wj; k < c.N; k += C::CB) t3_trial_node<M, I>(c, k, alpha, a1, a2);
         red[(0 * C::CB + wj) * I + wi] = a1;
         red[(1 * C::CB + wj) * I + wi] = a2;
     }
@@ -565,10 +583,11 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_>::THREADS) solve_kernel_t3(
     const bool valid = b >= io.b0 && b < io.b1;
     const int bi = valid ? b : io.b1 - 1;       // surplus slots read the last instance's inputs and never write outputs
 
-    T3Ctx<M> c(P);
+    T3Ctx<M, I> c(P);
     c.N = N;
-    c.V = W.V2 + (size_t)b * NV; c.LAM = W.LAM2 + (size_t)b * Mc;
-    c.DV = W.DV2 + (size_t)b * NV; c.LAMN = W.LAMN2 + (size_t)b * Mc;
+    // the iterate lives tile-wise, [element][instance]: every access of a warp is a run of full sectors whatever I is
+    c.V = W.V2 + (size_t)tile * I * NV + i; c.LAM = W.LAM2 + (size_t)tile * I * Mc + i;
+    c.DV = W.DV2 + (size_t)tile * I * NV + i; c.LAMN = W.LAMN2 + (size_t)tile * I * Mc + i;
     c.LINp = W.LIN2 + (size_t)b * C::LIN;
     c.traj = io.traj + (size_t)bi * N * NX;
     double* fg_tile = W.FG2 + (size_t)tile * I * N * C::FG;
@@ -583,17 +602,17 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_>::THREADS) solve_kernel_t3(
     // ---- start point (ModelControl.cpp:28-50,68 cold; :161 warm), x_0 pinned (:144-145); the C workers of an instance help ----
     const bool warm = io.warm_start && W.have_warm;
     if (worker) {
-        if (!warm) for (int e = NX + j; e < NV; e += C::CB) c.V[e] = 0.0;
-        if (!(warm && io.warm_start_duals)) for (int e = j; e < Mc; e += C::CB) c.LAM[e] = 0.0;
+        if (!warm) for (int e = NX + j; e < NV; e += C::CB) c.V[(size_t)e * I] = 0.0;
+        if (!(warm && io.warm_start_duals)) for (int e = j; e < Mc; e += C::CB) c.LAM[(size_t)e * I] = 0.0;
         for (int e = j; e < NX; e += C::CB) {
-            c.V[e] = io.state[(size_t)bi * NX + e];
-            c.DV[e] = 0.0;
+            c.V[(size_t)e * I] = io.state[(size_t)bi * NX + e];
+            c.DV[(size_t)e * I] = 0.0;
         }
     }
     __syncthreads();
     if (P.is_linear && tid < I) {
         double x0[NX], xd[NX], A[NX * NX], Bm[NX * NU];
-        MMPC_UNROLL for (int a = 0; a < NX; ++a) x0[a] = c.V[a];
+        MMPC_UNROLL for (int a = 0; a < NX; ++a) x0[a] = c.V[(size_t)a * I];
         M::fAB(x0, c.uinit, xd, A, Bm);
         MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) c.LINp[a] = A[a];
         MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) c.LINp[NX * NX + a] = Bm[a];
@@ -671,13 +690,13 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_>::THREADS) solve_kernel_t3(
             constexpr int UB = 8;
             for (int e0 = NX + j; e0 < NV; e0 += C::CB * UB) {
                 double vz[UB], vd[UB];
-                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) { vz[q] = Vp[e0 + q * C::CB]; vd[q] = DVp[e0 + q * C::CB]; }
-                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) Vp[e0 + q * C::CB] = fma(al, vd[q], vz[q]);
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) { vz[q] = Vp[(size_t)(e0 + q * C::CB) * I]; vd[q] = DVp[(size_t)(e0 + q * C::CB) * I]; }
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) Vp[(size_t)(e0 + q * C::CB) * I] = fma(al, vd[q], vz[q]);
             }
             for (int e0 = j; e0 < Mc; e0 += C::CB * UB) {
                 double vl[UB], vn[UB];
-                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) { vl[q] = LAMp[e0 + q * C::CB]; vn[q] = LAMNp[e0 + q * C::CB]; }
-                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) LAMp[e0 + q * C::CB] = fma(al, vn[q] - vl[q], vl[q]);
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) { vl[q] = LAMp[(size_t)(e0 + q * C::CB) * I]; vn[q] = LAMNp[(size_t)(e0 + q * C::CB) * I]; }
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) LAMp[(size_t)(e0 + q * C::CB) * I] = fma(al, vn[q] - vl[q], vl[q]);
             }
         }
         __syncthreads();
@@ -685,18 +704,18 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_>::THREADS) solve_kernel_t3(
 #ifdef MMPC_T3_PROFILE
     if (blockIdx.x == 0 && tid == 0) printf("[t3 kernel  ] loop %lld cycles, %d iterations\n", clock64() - t_kernel0, it);
 #endif
-    // ---- outputs: the iterate already is the reference's V layout ----
+    // ---- outputs: the reference's V layout, instance-major ----
     if (valid && worker) {
         double* Vo = io.V_out + (size_t)b * NV;
         constexpr int UB = 8;  // batched so that the loads of one batch are in flight together
         for (int e0 = j; e0 < NV; e0 += C::CB * UB) {
             double t[UB];
-            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) t[q] = Vp[e0 + q * C::CB];
+            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) t[q] = Vp[(size_t)(e0 + q * C::CB) * I];
             MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) __stcs(&Vo[e0 + q * C::CB], t[q]);
         }
         if (io.lam_out) for (int e0 = j; e0 < Mc; e0 += C::CB * UB) {
             double t[UB];
-            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) t[q] = LAMp[e0 + q * C::CB];
+            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) t[q] = LAMp[(size_t)(e0 + q * C::CB) * I];
             MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) __stcs(&io.lam_out[(size_t)b * Mc + e0 + q * C::CB], t[q]);
         }
     }
@@ -735,6 +754,7 @@ struct LaunchT3 {
         if (cfg == 2) return go<14, 8, 4>(P, W, io, st);
         if (cfg == 3) return go<16, 4, 4>(P, W, io, st);
         if (cfg == 4) return go<32, 4, 4>(P, W, io, st);
+        if (cfg == 5) return go<32, 7, 4>(P, W, io, st);
         return go<8, 4, 4>(P, W, io, st);
     }
 };
