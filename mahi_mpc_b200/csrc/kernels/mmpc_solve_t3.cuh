@@ -72,6 +72,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 // pattern of A and B (e.g. the kinematic rows q' = qdot), which the generator reports as bit masks.  In the fully unrolled
 // loops below the guards fold at compile time, so structurally zero products are never issued (CasADi's generated code
 // exploits the same sparsity).  Not valid for RK4 (fill-in); T3 is Euler/linearised only.
+// record stores: MMPC_T3_STREAM selects evict-first (st.global.cs) stores
+#ifdef MMPC_T3_STREAM
+#define T3_ST(p, v) __stcs((p), (v))
+#else
+#define T3_ST(p, v) (*(p) = (v))
+#endif
 #define T3_FXNZ(r, c) (((r) == (c)) || ((M::A_MASK >> ((r) * NX + (c))) & 1ULL))
 #define T3_FUNZ(r, c) ((M::B_MASK >> ((r) * NU + (c))) & 1ULL)
 // slot of flat entry a in the compacted storage (folds to a constant in the unrolled loops)
@@ -141,7 +147,7 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I>& c, int k, int
     double* const recp = rec + (size_t)j * C::RB * I + i;
     double* const fgp = fg_tile + (size_t)k * C::FG * I + i;
 #define T3_REC(f) recp[(f) * I]
-#define T3_FG(f, v) __stcs(&fgp[(f) * I], (v))  // streaming: records must not evict the iterate from L2
+#define T3_FG(f, v) T3_ST(&fgp[(f) * I], (v))  // streaming: records must not evict the iterate from L2
     double qe[NX], dual = 0.0, prim = 0.0, theta = 0.0, fval = 0.0, lam1 = 0.0;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         const double e = F[a] - r[a], cr = F[a] - xn[a];
@@ -220,9 +226,9 @@ __device__ __forceinline__ bool t3_riccati_stage(T3Riccati<M>& V, const double* 
     MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) Fu[a] = T3_FUNZ(a / NU, a % NU) ? T3_R(C::RB_FU + T3_FUSLOT(a)) : 0.0;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) cres[a] = T3_R(C::RB_C + a);
     // value function of stage k+1 -> global (the forward sweep needs it for lam_k)
-    MMPC_UNROLL for (int a = 0; a < NX; ++a) MMPC_UNROLL for (int b = a; b < NX; ++b) __stcs(&pg[(C::PG_XX + tri(a, b, NX)) * I], V.Pxx[a * NX + b]);
-    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) __stcs(&pg[(C::PG_XV + a) * I], V.Pxv[a]);
-    MMPC_UNROLL for (int a = 0; a < NX; ++a) __stcs(&pg[(C::PG_X + a) * I], V.px[a]);
+    MMPC_UNROLL for (int a = 0; a < NX; ++a) MMPC_UNROLL for (int b = a; b < NX; ++b) T3_ST(&pg[(C::PG_XX + tri(a, b, NX)) * I], V.Pxx[a * NX + b]);
+    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) T3_ST(&pg[(C::PG_XV + a) * I], V.Pxv[a]);
+    MMPC_UNROLL for (int a = 0; a < NX; ++a) T3_ST(&pg[(C::PG_X + a) * I], V.px[a]);
     double y[NX], yv[NU];
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         double t = V.px[a];
@@ -294,9 +300,9 @@ __device__ __forceinline__ bool t3_riccati_stage(T3Riccati<M>& V, const double* 
     }
     MMPC_UNROLL for (int b = 0; b < NU; ++b) k0[b] = -gu[b];
     chol_solve<NU>(Guu, k0);
-    MMPC_UNROLL for (int a = 0; a < NU * NX; ++a) __stcs(&kg[(C::KG_KX + a) * I], Kx[a]);
-    MMPC_UNROLL for (int a = 0; a < NU * NU; ++a) __stcs(&kg[(C::KG_KV + a) * I], Kv[a]);
-    MMPC_UNROLL for (int a = 0; a < NU; ++a) __stcs(&kg[(C::KG_K0 + a) * I], k0[a]);
+    MMPC_UNROLL for (int a = 0; a < NU * NX; ++a) T3_ST(&kg[(C::KG_KX + a) * I], Kx[a]);
+    MMPC_UNROLL for (int a = 0; a < NU * NU; ++a) T3_ST(&kg[(C::KG_KV + a) * I], Kv[a]);
+    MMPC_UNROLL for (int a = 0; a < NU; ++a) T3_ST(&kg[(C::KG_K0 + a) * I], k0[a]);
     const double qv0 = 0.0;
     (void)qv0;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
@@ -743,14 +749,16 @@ struct LaunchT3 {
         solve_kernel_t3<M, I_, CB_, CF_><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(P, W, io);
         return cudaGetLastError();
     }
-    // Configurations (tile width I, backward chunk CB, forward chunk CF):
-    //   A  8 x 4 x 4   64 threads, 41 KB: 4 CTAs/SM -- small batches, lowest latency
-    //   B 14 x 8 x 4  144 threads, 111 KB: 2 CTAs/SM -- wider backward chunks so that 8 Riccati stages cover the latency
-    //                  of one node evaluation in the worker warps
-    // kernel_variant = 3 + 256*k forces configuration k (1 = A, 2 = B) for experiments.
+    // Configurations (tile width I, backward chunk CB, forward chunk CF), measured at N = 50 (profiles/r1_t3_configs.txt):
+    //   1   8 x 4 x 4   64 threads, 41 KB, 4 CTAs/SM: lowest latency; best while the batch leaves at most two tiles per SM
+    //   5  32 x 7 x 4  256 threads, 194 KB, 1 CTA/SM: the serial warp is full (an fp64 instruction costs the same issue
+    //                  slots for 8 active lanes as for 32) and 7 worker warps evaluate 7 nodes at a time; best beyond that
+    //   2 14 x 8 x 4, 3 16 x 4 x 4, 4 32 x 4 x 4: experiments, slower
+    // The tile width fixes the layout of the persistent iterate, so the choice depends only on the batch size of the
+    // handle.  kernel_variant = 3 + 256*k forces configuration k.
     static cudaError_t run(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         const int forced = io.variant >> 8;
-        const int cfg = forced ? forced : 1;
+        const int cfg = forced ? forced : (W.B > 2 * 8 * 148 ? 5 : 1);
         if (cfg == 2) return go<14, 8, 4>(P, W, io, st);
         if (cfg == 3) return go<16, 4, 4>(P, W, io, st);
         if (cfg == 4) return go<32, 4, 4>(P, W, io, st);
