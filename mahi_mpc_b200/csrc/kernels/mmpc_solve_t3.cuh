@@ -22,14 +22,19 @@
 
 namespace mmpc {
 
-template <class M, int I_, int CB_, int CF_>
+template <class M, int I_, int CB_, int CF_, int SK_ = 0>
 struct T3 {
     static constexpr int NX = M::NX, NU = M::NU, S = NX + NU, N2 = NX + 2 * NU, NH = S * (S + 1) / 2;
     static constexpr int I = I_;    // instances per CTA (<= 32: one serial lane each)
     static constexpr int CB = CB_;  // nodes per chunk in the backward sweep (one node per worker thread)
     static constexpr int CF = CF_;  // nodes per chunk in the forward sweep (CF <= CB)
+    static_assert(CF_ <= CB_, "the forward chunk's merit evaluations use the backward chunk's worker slots");
     static constexpr int WORKERS = I * CB;
-    static constexpr int THREADS = 32 + WORKERS;
+    // SK: warp 4 idles, so that the serial warp (warp 0) has its SM sub-partition -- and its fp64 pipe -- to itself
+    static constexpr int SK = SK_;
+    static constexpr int THREADS = 32 + WORKERS + (SK ? 32 : 0);
+    __device__ static __forceinline__ bool is_worker(int tid) { return tid >= 32 && !(SK && tid >= 128 && tid < 160); }
+    __device__ static __forceinline__ int widx(int tid) { return tid - 32 - ((SK && tid >= 160) ? 32 : 0); }
     // Fx and Fu are stored compacted to their structural non-zeros (generator masks; dense if a mask does not fit 64 bits);
     // the value-function block Pxx is stored as its upper triangle
     static constexpr bool SPARSE = NX * NX <= 64 && NX * NU <= 64;
@@ -343,8 +348,8 @@ __device__ __noinline__ bool t3_backward(const T3Ctx<M, C::I>& cin, double* smem
     const T3Ctx<M, C::I> c = cin;  // callee-local copy: the context and all accumulators stay in registers (the caller's copy has
                              // its address taken and therefore lives in local memory)
     const int N = c.N;
-    const bool worker = tid >= 32;
-    const int w = tid - 32, wi = w % I, wj = w / I;
+    const bool worker = C::is_worker(tid);
+    const int w = C::widx(tid), wi = w % I, wj = w / I;
     double* dl = smem + C::SM_INST;  // per-instance delta, published by the serial lanes
     T3Riccati<M> V;
     MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) V.Pxx[a] = 0.0;
@@ -443,8 +448,8 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I>& cin, double* smem,
     const T3Ctx<M, C::I> c = cin;  // register-resident copies (see t3_backward)
     T3Fwd o;
     const int N = c.N;
-    const bool worker = tid >= 32;
-    const int w = tid - 32, wi = w % I, wj = w / I;
+    const bool worker = C::is_worker(tid);
+    const int w = C::widx(tid), wi = w % I, wj = w / I;
     double* red = smem + C::SM_RED;
     double dx[NX], dv[NU];
     MMPC_UNROLL for (int a = 0; a < NX; ++a) dx[a] = 0.0;
@@ -555,8 +560,8 @@ template <class M, class C>
 __device__ __noinline__ void t3_trial(const T3Ctx<M, C::I>& cin, double* smem, int tid, double& f1, double& th1) {
     constexpr int I = C::I;
     const T3Ctx<M, C::I> c = cin;
-    const bool worker = tid >= 32;
-    const int w = tid - 32, wi = w % I, wj = w / I;
+    const bool worker = C::is_worker(tid);
+    const int w = C::widx(tid), wi = w % I, wj = w / I;
     double* red = smem + C::SM_RED;
     if (worker) {
         const double alpha = smem[C::SM_INST + I + wi];
@@ -574,16 +579,16 @@ __device__ __noinline__ void t3_trial(const T3Ctx<M, C::I>& cin, double* smem, i
     __syncthreads();
 }
 
-template <class M, int I_, int CB_, int CF_>
-__global__ void __launch_bounds__(T3<M, I_, CB_, CF_>::THREADS) solve_kernel_t3(mmpc_problem P, mmpc_workspace W, mmpc_solve_io io) {
-    using C = T3<M, I_, CB_, CF_>;
+template <class M, int I_, int CB_, int CF_, int SK_>
+__global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_>::THREADS) solve_kernel_t3(mmpc_problem P, mmpc_workspace W, mmpc_solve_io io) {
+    using C = T3<M, I_, CB_, CF_, SK_>;
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, tile = io.b0 / C::I + blockIdx.x;  // b0 is a multiple of 32*I-compatible tile starts
-    const bool worker = tid >= 32;
+    const bool worker = C::is_worker(tid);
     // a thread's instance: serial lane tid -> instance tid; worker w -> instance w % I (node slot w / I)
-    const int i = worker ? (tid - 32) % I : (tid < I ? tid : 0);
-    const int j = worker ? (tid - 32) / I : 0;
+    const int i = worker ? C::widx(tid) % I : (tid < I ? tid : 0);
+    const int j = worker ? C::widx(tid) / I : 0;
     const int N = P.N, NV = NX * (N + 1) + NU * N, Mc = N * NX;
     const int b = tile * I + i;                 // workspace slot (arrays are sized for the batch padded to 32)
     const bool valid = b >= io.b0 && b < io.b1;
@@ -735,34 +740,31 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_>::THREADS) solve_kernel_t3(
 
 template <class M>
 struct LaunchT3 {
-    template <int I_, int CB_, int CF_>
+    template <int I_, int CB_, int CF_, int SK_ = 0>
     static cudaError_t go(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
-        using C = T3<M, I_, CB_, CF_>;
+        using C = T3<M, I_, CB_, CF_, SK_>;
         static bool attr_done = false;
         if (!attr_done && C::SMEM_BYTES > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(solve_kernel_t3<M, I_, CB_, CF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+            cudaError_t e = cudaFuncSetAttribute(solve_kernel_t3<M, I_, CB_, CF_, SK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
             if (e != cudaSuccess) return e;
             attr_done = true;
         }
         const int t0 = io.b0 / C::I, t1 = (io.b1 + C::I - 1) / C::I;  // tiles touched by [b0, b1)
         const int grid = t1 - t0;
-        solve_kernel_t3<M, I_, CB_, CF_><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(P, W, io);
+        solve_kernel_t3<M, I_, CB_, CF_, SK_><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(P, W, io);
         return cudaGetLastError();
     }
     // Configurations (tile width I, backward chunk CB, forward chunk CF), measured at N = 50 (profiles/r1_t3_configs.txt):
-    //   1   8 x 4 x 4   64 threads, 41 KB, 4 CTAs/SM: lowest latency; best while the batch leaves at most two tiles per SM
-    //   5  32 x 7 x 4  256 threads, 194 KB, 1 CTA/SM: the serial warp is full (an fp64 instruction costs the same issue
+    //   1   8 x 4 x 4   64 threads,  41 KB, 4 CTAs/SM: lowest latency; best while the batch leaves at most two tiles per SM
+    //   2  32 x 7 x 5  256 threads, 182 KB, 1 CTA/SM: the serial warp is full (an fp64 instruction costs the same issue
     //                  slots for 8 active lanes as for 32) and 7 worker warps evaluate 7 nodes at a time; best beyond that
-    //   2 14 x 8 x 4, 3 16 x 4 x 4, 4 32 x 4 x 4: experiments, slower
+    // Tried and slower: 14 x 8 x 4, 16 x 4 x 4, 32 x 4 x 4, 32 x 7 x {4, 6}, 32 x 6 x {4, 5} with warp 4 idle (SK).
     // The tile width fixes the layout of the persistent iterate, so the choice depends only on the batch size of the
     // handle.  kernel_variant = 3 + 256*k forces configuration k.
     static cudaError_t run(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         const int forced = io.variant >> 8;
-        const int cfg = forced ? forced : (W.B > 2 * 8 * 148 ? 5 : 1);
-        if (cfg == 2) return go<14, 8, 4>(P, W, io, st);
-        if (cfg == 3) return go<16, 4, 4>(P, W, io, st);
-        if (cfg == 4) return go<32, 4, 4>(P, W, io, st);
-        if (cfg == 5) return go<32, 7, 4>(P, W, io, st);
+        const int cfg = forced ? forced : (W.B > 2 * 8 * 148 ? 2 : 1);
+        if (cfg == 2) return go<32, 7, 5>(P, W, io, st);
         return go<8, 4, 4>(P, W, io, st);
     }
 };
