@@ -16,7 +16,7 @@
 //   * the two run concurrently on double-buffered records: one __syncthreads per chunk, no other synchronisation.
 // One launch per batched solve; no grid-wide synchronisation.  Replaces IPOPT+MUMPS at ModelControl.cpp:159.
 #pragma once
-#ifdef MMPC_T3_PROFILE
+#if defined(MMPC_T3_PROFILE) || defined(MMPC_T3_PROFILE_SWEEPS)
 #include <cstdio>
 #endif
 
@@ -68,6 +68,9 @@ struct T3 {
     static constexpr int LIN = NX * NX + NX * NU + NX;
 };
 
+// CTA-wide barrier usable from role-specific code paths (every thread of the CTA executes the same NUMBER of these;
+// bar.sync counts arrivals per barrier, not per call site)
+__device__ __forceinline__ void t3_cta_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
@@ -77,11 +80,21 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 // pattern of A and B (e.g. the kinematic rows q' = qdot), which the generator reports as bit masks.  In the fully unrolled
 // loops below the guards fold at compile time, so structurally zero products are never issued (CasADi's generated code
 // exploits the same sparsity).  Not valid for RK4 (fill-in); T3 is Euler/linearised only.
-// record stores: MMPC_T3_STREAM selects evict-first (st.global.cs) stores
-#ifdef MMPC_T3_STREAM
+// record stores.  MMPC_T3_ST: 0 plain, 1 evict-first (st.global.cs), 2 L2 evict-last
+#ifndef MMPC_T3_ST
+#define MMPC_T3_ST 0
+#endif
+__device__ __forceinline__ void t3_st_evict_last(double* p, double v) {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+#if MMPC_T3_ST == 0
+#define T3_ST(p, v) (*(p) = (v))
+#elif MMPC_T3_ST == 1
 #define T3_ST(p, v) __stcs((p), (v))
 #else
-#define T3_ST(p, v) (*(p) = (v))
+#define T3_ST(p, v) t3_st_evict_last((p), (v))
 #endif
 #define T3_FXNZ(r, c) (((r) == (c)) || ((M::A_MASK >> ((r) * NX + (c))) & 1ULL))
 #define T3_FUNZ(r, c) ((M::B_MASK >> ((r) * NU + (c))) & 1ULL)
@@ -152,7 +165,7 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I>& c, int k, int
     double* const recp = rec + (size_t)j * C::RB * I + i;
     double* const fgp = fg_tile + (size_t)k * C::FG * I + i;
 #define T3_REC(f) recp[(f) * I]
-#define T3_FG(f, v) T3_ST(&fgp[(f) * I], (v))  // streaming: records must not evict the iterate from L2
+#define T3_FG(f, v) T3_ST(&fgp[(f) * I], (v))
     double qe[NX], dual = 0.0, prim = 0.0, theta = 0.0, fval = 0.0, lam1 = 0.0;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         const double e = F[a] - r[a], cr = F[a] - xn[a];
@@ -351,54 +364,69 @@ __device__ __noinline__ bool t3_backward(const T3Ctx<M, C::I>& cin, double* smem
     const bool worker = C::is_worker(tid);
     const int w = C::widx(tid), wi = w % I, wj = w / I;
     double* dl = smem + C::SM_INST;  // per-instance delta, published by the serial lanes
-    T3Riccati<M> V;
-    MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) V.Pxx[a] = 0.0;
-    MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) V.Pxv[a] = 0.0;
-    MMPC_UNROLL for (int a = 0; a < NU * NU; ++a) V.Pvv[a] = 0.0;
-    MMPC_UNROLL for (int a = 0; a < NX; ++a) V.px[a] = 0.0;
-    MMPC_UNROLL for (int a = 0; a < NU; ++a) V.pv[a] = 0.0;
     double n_dual = 0.0, n_prim = 0.0, n_theta = 0.0, n_fval = 0.0, n_lam = 0.0;
     bool ok = true;
     if (tid < I) dl[tid] = delta_self;
     __syncthreads();
-    const double delta = worker ? dl[wi] : 0.0;
     const int nch = (N + C::CB - 1) / C::CB;
-#ifdef MMPC_T3_PROFILE
+#ifdef MMPC_T3_PROFILE_SWEEPS
     long long t_work = 0, t_all0 = clock64();
 #endif
     // step = nch: workers evaluate the last chunk (prologue); step = ch < nch: warp 0 consumes chunk ch while the workers
-    // evaluate chunk ch-1 (one call site, so the evaluator is inlined exactly once)
-    for (int step = nch; step >= 0; --step) {
-#ifdef MMPC_T3_PROFILE
-        const long long t0 = clock64();
+    // evaluate chunk ch-1.  The two roles run their own copy of the step loop (same trip count, one CTA barrier per step):
+    // the Riccati state then is not live across the evaluator and the evaluator's temporaries are not live across the
+    // recursion, which is worth ~70 registers to each side.
+    if (worker) {
+        const double delta = dl[wi];
+        for (int step = nch; step >= 0; --step) {
+#ifdef MMPC_T3_PROFILE_SWEEPS
+            const long long t0 = clock64();
 #endif
-        if (worker) {
             const int ch = step - 1;
             if (ch >= 0) {
                 const int k0 = (int)((long long)ch * N / nch), kn = (int)((long long)(ch + 1) * N / nch) - k0;  // balanced chunks (<= CB nodes)
                 if (ch > 0 && wj < k0 - (int)((long long)(ch - 1) * N / nch)) t3_prefetch_node<M, C>(c, (int)((long long)(ch - 1) * N / nch) + wj);
                 if (wj < kn) t3_eval_node<M, C>(c, k0 + wj, wi, wj, delta, smem + C::SM_REC + (ch & 1) * C::BUF, smem + C::SM_RED + (ch & 1) * C::REDBUF, fg_tile);
             }
-        } else if (tid < I && step < nch) {
-            const int ch = step, k0 = (int)((long long)ch * N / nch), kn = (int)((long long)(ch + 1) * N / nch) - k0;
-            const double* rec = smem + C::SM_REC + (ch & 1) * C::BUF;
-            const double* red = smem + C::SM_RED + (ch & 1) * C::REDBUF;
-            for (int s = kn - 1; s >= 0; --s) {
-                const int k = k0 + s;
-                ok = t3_riccati_stage<M, C>(V, rec, s, tid, c.R, kg_tile + (size_t)k * C::KG * I + tid, pg_tile + (size_t)k * C::PG * I + tid) && ok;
-                n_dual = fmax(n_dual, red[(0 * C::CB + s) * I + tid]);
-                n_prim = fmax(n_prim, red[(1 * C::CB + s) * I + tid]);
-                n_theta += red[(2 * C::CB + s) * I + tid];
-                n_fval += red[(3 * C::CB + s) * I + tid];
-                n_lam += red[(4 * C::CB + s) * I + tid];
-            }
-        }
-#ifdef MMPC_T3_PROFILE
-        t_work += clock64() - t0;
+#ifdef MMPC_T3_PROFILE_SWEEPS
+            t_work += clock64() - t0;
 #endif
-        __syncthreads();
+            t3_cta_barrier();
+        }
+    } else {
+        T3Riccati<M> V;
+        MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) V.Pxx[a] = 0.0;
+        MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) V.Pxv[a] = 0.0;
+        MMPC_UNROLL for (int a = 0; a < NU * NU; ++a) V.Pvv[a] = 0.0;
+        MMPC_UNROLL for (int a = 0; a < NX; ++a) V.px[a] = 0.0;
+        MMPC_UNROLL for (int a = 0; a < NU; ++a) V.pv[a] = 0.0;
+        double R[NU];
+        MMPC_UNROLL for (int a = 0; a < NU; ++a) R[a] = c.R[a];
+        for (int step = nch; step >= 0; --step) {
+#ifdef MMPC_T3_PROFILE_SWEEPS
+            const long long t0 = clock64();
+#endif
+            if (tid < I && step < nch) {
+                const int ch = step, k0 = (int)((long long)ch * N / nch), kn = (int)((long long)(ch + 1) * N / nch) - k0;
+                const double* rec = smem + C::SM_REC + (ch & 1) * C::BUF;
+                const double* red = smem + C::SM_RED + (ch & 1) * C::REDBUF;
+                for (int s = kn - 1; s >= 0; --s) {
+                    const int k = k0 + s;
+                    ok = t3_riccati_stage<M, C>(V, rec, s, tid, R, kg_tile + (size_t)k * C::KG * I + tid, pg_tile + (size_t)k * C::PG * I + tid) && ok;
+                    n_dual = fmax(n_dual, red[(0 * C::CB + s) * I + tid]);
+                    n_prim = fmax(n_prim, red[(1 * C::CB + s) * I + tid]);
+                    n_theta += red[(2 * C::CB + s) * I + tid];
+                    n_fval += red[(3 * C::CB + s) * I + tid];
+                    n_lam += red[(4 * C::CB + s) * I + tid];
+                }
+            }
+#ifdef MMPC_T3_PROFILE_SWEEPS
+            t_work += clock64() - t0;
+#endif
+            t3_cta_barrier();
+        }
     }
-#ifdef MMPC_T3_PROFILE
+#ifdef MMPC_T3_PROFILE_SWEEPS
     if (blockIdx.x == 0 && (tid == 0 || tid == 32))
         printf("[t3 backward] tid %d busy %lld of %lld cycles (%d chunks of %d)\n", tid, t_work, clock64() - t_all0, nch, C::CB);
 #endif
@@ -475,7 +503,7 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I>& cin, double* smem,
         const int k0 = ch * C::CF, kn = min(C::CF, N - k0);
         if (wj < kn) t3_trial_node<M, I>(c, k0 + wj, 1.0, f1, th1);
     };
-#ifdef MMPC_T3_PROFILE
+#ifdef MMPC_T3_PROFILE_SWEEPS
     long long t_work = 0, t_all0 = clock64();
 #endif
     if (worker) {
@@ -484,7 +512,7 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I>& cin, double* smem,
     }
     __syncthreads();
     for (int ch = 0; ch < nch; ++ch) {
-#ifdef MMPC_T3_PROFILE
+#ifdef MMPC_T3_PROFILE_SWEEPS
         const long long t0 = clock64();
 #endif
         if (worker) {
@@ -532,12 +560,12 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I>& cin, double* smem,
                 MMPC_UNROLL for (int a = 0; a < NU; ++a) dv[a] = du[a];
             }
         }
-#ifdef MMPC_T3_PROFILE
+#ifdef MMPC_T3_PROFILE_SWEEPS
         t_work += clock64() - t0;
 #endif
         __syncthreads();  // the step of chunk ch is visible to the workers; buffer (ch+1)&1 is staged
     }
-#ifdef MMPC_T3_PROFILE
+#ifdef MMPC_T3_PROFILE_SWEEPS
     if (blockIdx.x == 0 && (tid == 0 || tid == 32))
         printf("[t3 forward ] tid %d busy %lld of %lld cycles (%d chunks of %d)\n", tid, t_work, clock64() - t_all0, nch, C::CF);
 #endif
@@ -584,6 +612,10 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_>::THREADS) solve_kerne
     using C = T3<M, I_, CB_, CF_, SK_>;
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
     extern __shared__ __align__(16) double smem[];
+#ifdef MMPC_T3_PROFILE
+    const long long t_entry = clock64();
+    long long t_bwd[8] = {0}, t_fwd[8] = {0}, t_post[8] = {0};
+#endif
     const int tid = threadIdx.x, tile = io.b0 / C::I + blockIdx.x;  // b0 is a multiple of 32*I-compatible tile starts
     const bool worker = C::is_worker(tid);
     // a thread's instance: serial lane tid -> instance tid; worker w -> instance w % I (node slot w / I)
@@ -647,7 +679,13 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_>::THREADS) solve_kerne
     for (it = 0;; ++it) {
         T3Norms nrm;
         double delta = 0.0;
+#ifdef MMPC_T3_PROFILE
+        const long long tp0 = clock64();
+#endif
         bool ok = t3_backward<M, C>(c, smem, tid, delta, nrm, fg_tile, kg_tile, pg_tile);
+#ifdef MMPC_T3_PROFILE
+        if (it < 8) t_bwd[it] = clock64() - tp0;
+#endif
         if (active) {
             const double sd = fmax(100.0, nrm.lam_l1 / (double)(nfree + ncon)) / 100.0;  // IPOPT s_d, s_max = 100 [upstream]
             err = fmax(nrm.dual_inf / sd, nrm.prim_inf);
@@ -675,7 +713,14 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_>::THREADS) solve_kerne
         if (delta > 0.0) delta_last = delta;
         if (!__syncthreads_or(active)) break;
         T3Fwd fo;
+#ifdef MMPC_T3_PROFILE
+        const long long tp1 = clock64();
+#endif
         t3_forward<M, C>(c, smem, tid, fo, fg_tile, kg_tile, pg_tile);
+#ifdef MMPC_T3_PROFILE
+        const long long tp2 = clock64();
+        if (it < 8) t_fwd[it] = tp2 - tp1;
+#endif
         if (active && !(fo.finite && isfinite(fo.f1))) { status = MMPC_SOLVE_NUMERICAL; active = false; }
         nu_merit = fmax(nu_merit, 1.1 * fo.lam_inf + 1e-8);
         const double m0 = nrm.fval + nu_merit * nrm.theta;
@@ -711,9 +756,12 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_>::THREADS) solve_kerne
             }
         }
         __syncthreads();
+#ifdef MMPC_T3_PROFILE
+        if (it < 8) t_post[it] = clock64() - tp2;
+#endif
     }
 #ifdef MMPC_T3_PROFILE
-    if (blockIdx.x == 0 && tid == 0) printf("[t3 kernel  ] loop %lld cycles, %d iterations\n", clock64() - t_kernel0, it);
+    const long long t_loop_end = clock64();
 #endif
     // ---- outputs: the reference's V layout, instance-major ----
     if (valid && worker) {
@@ -736,6 +784,14 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_>::THREADS) solve_kerne
         s.ls_steps = ls_total; s.reg_steps = reg_total;
         io.stats[b] = s;
     }
+#ifdef MMPC_T3_PROFILE
+    __syncthreads();
+    if (blockIdx.x == 0 && tid == 0) {
+        const long long t_end = clock64();
+        printf("[t3 kernel] prologue %lld  loop %lld  epilogue %lld cycles, %d iterations\n", t_kernel0 - t_entry, t_loop_end - t_kernel0, t_end - t_loop_end, it);
+        for (int q = 0; q <= it && q < 8; ++q) printf("[t3 it %d] backward %lld  forward %lld  line search + step %lld\n", q, t_bwd[q], t_fwd[q], t_post[q]);
+    }
+#endif
 }
 
 template <class M>
