@@ -22,7 +22,7 @@
 
 namespace mmpc {
 
-template <class M, int I_, int CB_, int CF_, int SK_ = 0>
+template <class M, int I_, int CB_, int CF_, int SK_ = 0, int RK_ = 0>
 struct T3 {
     static constexpr int NX = M::NX, NU = M::NU, S = NX + NU, N2 = NX + 2 * NU, NH = S * (S + 1) / 2;
     static constexpr int I = I_;    // instances per CTA (<= 32: one serial lane each)
@@ -37,7 +37,8 @@ struct T3 {
     __device__ static __forceinline__ int widx(int tid) { return tid - 32 - ((SK && tid >= 160) ? 32 : 0); }
     // Fx and Fu are stored compacted to their structural non-zeros (generator masks; dense if a mask does not fit 64 bits);
     // the value-function block Pxx is stored as its upper triangle
-    static constexpr bool SPARSE = NX * NX <= 64 && NX * NU <= 64;
+    static constexpr int RK = RK_;  // RK4 shooting intervals: dense sensitivities (the one-step masks below hold for Euler / linearised steps only)
+    static constexpr bool SPARSE = !RK_ && NX * NX <= 64 && NX * NU <= 64;
     static constexpr unsigned long long fx_mask() {
         unsigned long long m = SPARSE ? M::A_MASK : ~0ULL;
         if (SPARSE) for (int i = 0; i < NX; ++i) m |= 1ULL << (i * NX + i);
@@ -96,13 +97,13 @@ __device__ __forceinline__ void t3_st_evict_last(double* p, double v) {
 #else
 #define T3_ST(p, v) t3_st_evict_last((p), (v))
 #endif
-#define T3_FXNZ(r, c) (((r) == (c)) || ((M::A_MASK >> ((r) * NX + (c))) & 1ULL))
-#define T3_FUNZ(r, c) ((M::B_MASK >> ((r) * NU + (c))) & 1ULL)
+#define T3_FXNZ(r, c) (!C::SPARSE || ((C::FXM >> ((r) * NX + (c))) & 1ULL))
+#define T3_FUNZ(r, c) (!C::SPARSE || ((C::FUM >> ((r) * NU + (c))) & 1ULL))
 // slot of flat entry a in the compacted storage (folds to a constant in the unrolled loops)
 #define T3_FXSLOT(a) (C::SPARSE ? __popcll(C::FXM & ((1ULL << (a)) - 1ULL)) : (a))
 #define T3_FUSLOT(a) (C::SPARSE ? __popcll(C::FUM & ((1ULL << (a)) - 1ULL)) : (a))
 
-template <class M, int I_>
+template <class M, int I_, int RK_ = 0>
 struct T3Ctx {
     static constexpr int NX = M::NX, NU = M::NU, S = NX + NU, I = I_;
     const mmpc_problem& P;
@@ -119,6 +120,9 @@ struct T3Ctx {
             double x0[NX];
             MMPC_UNROLL for (int i = 0; i < NX; ++i) x0[i] = V[(size_t)i * I];
             step_linear<M, WANT>(P.h, x, u, LINp, LINp + NX * NX, LINp + NX * NX + NX * NU, x0, uinit, F, Fx, Fu, Hs);
+        } else if (RK_) {
+            step_rk4<M, (WANT >= 1 ? 1 : 0)>(P.h, P.substeps, x, u, F, Fx, Fu);
+            if (WANT >= 2) MMPC_UNROLL for (int i = 0; i < S * (S + 1) / 2; ++i) Hs[i] = 0.0;  // Gauss-Newton Hessian under RK4
         } else {
             step_euler<M, WANT>(P.h, x, u, wq, r, lam, F, Fx, Fu, Hs);
         }
@@ -129,7 +133,7 @@ struct T3Ctx {
 // starts with a dependent chain of L2 round trips)
 __device__ __forceinline__ void t3_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 template <class M, class C>
-__device__ __forceinline__ void t3_prefetch_node(const T3Ctx<M, C::I>& c, int k) {
+__device__ __forceinline__ void t3_prefetch_node(const T3Ctx<M, C::I, C::RK>& c, int k) {
     constexpr int NX = M::NX, S = C::S, I = C::I;
     const double* z = c.V + (size_t)k * S * I;
     MMPC_UNROLL for (int a = 0; a < S + NX; ++a) t3_prefetch(z + a * I);  // x_k, u_k, x_{k+1}; u_{k-1} and u_{k+1} belong to the neighbours
@@ -140,7 +144,7 @@ __device__ __forceinline__ void t3_prefetch_node(const T3Ctx<M, C::I>& c, int k)
 // ---- parallel phase of the backward sweep: thread (i, j) evaluates node k = k0 + j of instance i -------------
 // red slots: 0 dual_inf(max) 1 prim_inf(max) 2 theta 3 fval 4 lam_l1
 template <class M, class C>
-__device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I>& c, int k, int i, int j, double delta, double* rec, double* red,
+__device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I, C::RK>& c, int k, int i, int j, double delta, double* rec, double* red,
                                              double* fg_tile) {
     constexpr int NX = M::NX, NU = M::NU, S = C::S, NH = C::NH, I = C::I;
     const int N = c.N;
@@ -355,10 +359,10 @@ struct T3Norms {
 // lane per instance) the worker warps evaluate chunk ch-1 into the other record buffer.
 // returns (valid on the serial lanes) whether every G_uu was positive definite
 template <class M, class C>
-__device__ __noinline__ bool t3_backward(const T3Ctx<M, C::I>& cin, double* smem, int tid, double delta_self, T3Norms& nrm_out,
+__device__ __noinline__ bool t3_backward(const T3Ctx<M, C::I, C::RK>& cin, double* smem, int tid, double delta_self, T3Norms& nrm_out,
                                          double* fg_tile, double* kg_tile, double* pg_tile) {
     constexpr int NX = M::NX, NU = M::NU, I = C::I;
-    const T3Ctx<M, C::I> c = cin;  // callee-local copy: the context and all accumulators stay in registers (the caller's copy has
+    const T3Ctx<M, C::I, C::RK> c = cin;  // callee-local copy: the context and all accumulators stay in registers (the caller's copy has
                              // its address taken and therefore lives in local memory)
     const int N = c.N;
     const bool worker = C::is_worker(tid);
@@ -435,8 +439,8 @@ __device__ __noinline__ bool t3_backward(const T3Ctx<M, C::I>& cin, double* smem
 }
 
 // merit pieces of node k at z + alpha dz
-template <class M, int I>
-__device__ __forceinline__ void t3_trial_node(const T3Ctx<M, I>& c, int k, double alpha, double& f1, double& th1) {
+template <class M, int I, int RK>
+__device__ __forceinline__ void t3_trial_node(const T3Ctx<M, I, RK>& c, int k, double alpha, double& f1, double& th1) {
     constexpr int NX = M::NX, NU = M::NU, S = NX + NU;
     const double* z = c.V + (size_t)k * S * I;
     const double* d = c.DV + (size_t)k * S * I;
@@ -470,10 +474,10 @@ struct T3Fwd {
 // forward sweep for the tile, software pipelined: while warp 0 rolls the step through chunk ch, the worker warps stage
 // chunk ch+1's records (cp.async) and evaluate the merit terms of the full step on chunk ch-1.
 template <class M, class C>
-__device__ __noinline__ void t3_forward(const T3Ctx<M, C::I>& cin, double* smem, int tid, T3Fwd& o_out, const double* fg_tile, const double* kg_tile,
+__device__ __noinline__ void t3_forward(const T3Ctx<M, C::I, C::RK>& cin, double* smem, int tid, T3Fwd& o_out, const double* fg_tile, const double* kg_tile,
                                         const double* pg_tile) {
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
-    const T3Ctx<M, C::I> c = cin;  // register-resident copies (see t3_backward)
+    const T3Ctx<M, C::I, C::RK> c = cin;  // register-resident copies (see t3_backward)
     T3Fwd o;
     const int N = c.N;
     const bool worker = C::is_worker(tid);
@@ -501,7 +505,7 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I>& cin, double* smem,
     double f1 = 0.0, th1 = 0.0;  // worker-local merit sums
     auto trial_chunk = [&](int ch) {  // workers with node slot < CF take part
         const int k0 = ch * C::CF, kn = min(C::CF, N - k0);
-        if (wj < kn) t3_trial_node<M, I>(c, k0 + wj, 1.0, f1, th1);
+        if (wj < kn) t3_trial_node<M, I, C::RK>(c, k0 + wj, 1.0, f1, th1);
     };
 #ifdef MMPC_T3_PROFILE_SWEEPS
     long long t_work = 0, t_all0 = clock64();
@@ -585,16 +589,16 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I>& cin, double* smem,
 
 // merit of z + alpha_i dz for every instance of the tile (alpha per instance in shared memory)
 template <class M, class C>
-__device__ __noinline__ void t3_trial(const T3Ctx<M, C::I>& cin, double* smem, int tid, double& f1, double& th1) {
+__device__ __noinline__ void t3_trial(const T3Ctx<M, C::I, C::RK>& cin, double* smem, int tid, double& f1, double& th1) {
     constexpr int I = C::I;
-    const T3Ctx<M, C::I> c = cin;
+    const T3Ctx<M, C::I, C::RK> c = cin;
     const bool worker = C::is_worker(tid);
     const int w = C::widx(tid), wi = w % I, wj = w / I;
     double* red = smem + C::SM_RED;
     if (worker) {
         const double alpha = smem[C::SM_INST + I + wi];
         double a1 = 0.0, a2 = 0.0;
-        for (int k = wj; k < c.N; k += C::CB) t3_trial_node<M, I>(c, k, alpha, a1, a2);
+        for (int k = wj; k < c.N; k += C::CB) t3_trial_node<M, I, C::RK>(c, k, alpha, a1, a2);
         red[(0 * C::CB + wj) * I + wi] = a1;
         red[(1 * C::CB + wj) * I + wi] = a2;
     }
@@ -607,9 +611,9 @@ __device__ __noinline__ void t3_trial(const T3Ctx<M, C::I>& cin, double* smem, i
     __syncthreads();
 }
 
-template <class M, int I_, int CB_, int CF_, int SK_>
-__global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_>::THREADS) solve_kernel_t3(mmpc_problem P, mmpc_workspace W, mmpc_solve_io io) {
-    using C = T3<M, I_, CB_, CF_, SK_>;
+template <class M, int I_, int CB_, int CF_, int SK_, int RK_>
+__global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_kernel_t3(mmpc_problem P, mmpc_workspace W, mmpc_solve_io io) {
+    using C = T3<M, I_, CB_, CF_, SK_, RK_>;
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
     extern __shared__ __align__(16) double smem[];
 #ifdef MMPC_T3_PROFILE
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_>::THREADS) solve_kerne
     const bool valid = b >= io.b0 && b < io.b1;
     const int bi = valid ? b : io.b1 - 1;       // surplus slots read the last instance's inputs and never write outputs
 
-    T3Ctx<M, I> c(P);
+    T3Ctx<M, I, C::RK> c(P);
     c.N = N;
     // the iterate lives tile-wise, [element][instance]: every access of a warp is a run of full sectors whatever I is
     c.V = W.V2 + (size_t)tile * I * NV + i; c.LAM = W.LAM2 + (size_t)tile * I * Mc + i;
@@ -796,18 +800,18 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_>::THREADS) solve_kerne
 
 template <class M>
 struct LaunchT3 {
-    template <int I_, int CB_, int CF_, int SK_ = 0>
+    template <int I_, int CB_, int CF_, int SK_ = 0, int RK_ = 0>
     static cudaError_t go(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
-        using C = T3<M, I_, CB_, CF_, SK_>;
+        using C = T3<M, I_, CB_, CF_, SK_, RK_>;
         static bool attr_done = false;
         if (!attr_done && C::SMEM_BYTES > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(solve_kernel_t3<M, I_, CB_, CF_, SK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+            cudaError_t e = cudaFuncSetAttribute(solve_kernel_t3<M, I_, CB_, CF_, SK_, RK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
             if (e != cudaSuccess) return e;
             attr_done = true;
         }
         const int t0 = io.b0 / C::I, t1 = (io.b1 + C::I - 1) / C::I;  // tiles touched by [b0, b1)
         const int grid = t1 - t0;
-        solve_kernel_t3<M, I_, CB_, CF_, SK_><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(P, W, io);
+        solve_kernel_t3<M, I_, CB_, CF_, SK_, RK_><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(P, W, io);
         return cudaGetLastError();
     }
     // Configurations (tile width I, backward chunk CB, forward chunk CF), measured at N = 50 (profiles/r1_t3_configs.txt):
@@ -820,6 +824,15 @@ struct LaunchT3 {
     static cudaError_t run(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         const int forced = io.variant >> 8;
         const int cfg = forced ? forced : (W.B > 2 * 8 * 148 ? 2 : 1);
+        if (P.integrator == MMPC_RK4 && !P.is_linear) {
+            // RK4 shooting (dense sensitivities, Gauss-Newton Hessian); instantiated for the small models T3 is the default for
+            if constexpr (M::NX + 2 * M::NU <= 8) {
+                if (cfg == 2) return go<32, 7, 5, 0, 1>(P, W, io, st);
+                return go<8, 4, 4, 0, 1>(P, W, io, st);
+            } else {
+                return cudaErrorNotSupported;
+            }
+        }
         if (cfg == 2) return go<32, 7, 5>(P, W, io, st);
         return go<8, 4, 4>(P, W, io, st);
     }

@@ -412,14 +412,16 @@ def test_rk4_nlp_and_solve_vs_oracle(api):
         assert abs(out["f"][b] - f) <= EVAL_RTOL * abs(f) and rel(out["g"][b], g) < EVAL_RTOL and rel(out["grad_f"][b], gf) < EVAL_RTOL
         for k in range(N):
             assert rel(out["Fx"][b, k], J[k * 4:(k + 1) * 4, k * 6:k * 6 + 4]) < EVAL_RTOL
-    s = api.Solver(m, B, tol=1e-9, integrator=api.RK4, substeps=2)
-    s.set_weights(Q, R, Rm)
-    Vs, lam, st = s.solve(x0, up, traj)
-    assert (st["status"] == 0).all(), st
-    for b in range(B):
-        r = nlp.solve(P, x0[b], p[b], tol=1e-10, max_iter=400)
-        assert r.status == 0
-        assert np.abs(Vs[b] - r.V).max() < U_ATOL and abs(st["objective"][b] - r.f) <= OBJ_RTOL * abs(r.f)
+    ref = [nlp.solve(P, x0[b], p[b], tol=1e-10, max_iter=400) for b in range(B)]
+    assert all(r.status == 0 for r in ref)
+    # default (T3, thread-block tiles), T1 (thread per instance) and T3's 32-instance tile configuration
+    for variant in (0, 1, 3 + 256 * 2):
+        s = api.Solver(m, B, tol=1e-9, integrator=api.RK4, substeps=2, kernel_variant=variant)
+        s.set_weights(Q, R, Rm)
+        Vs, lam, st = s.solve(x0, up, traj)
+        assert (st["status"] == 0).all(), (variant, st)
+        for b, r in enumerate(ref):
+            assert np.abs(Vs[b] - r.V).max() < U_ATOL and abs(st["objective"][b] - r.f) <= OBJ_RTOL * abs(r.f), variant
 
 
 @pytest.mark.parametrize("plant", ["rk4", "euler"])
