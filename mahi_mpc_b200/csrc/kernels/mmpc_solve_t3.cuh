@@ -444,7 +444,8 @@ __device__ __forceinline__ void t3_trial_node(const T3Ctx<M, I, RK>& c, int k, d
     constexpr int NX = M::NX, NU = M::NU, S = NX + NU;
     const double* z = c.V + (size_t)k * S * I;
     const double* d = c.DV + (size_t)k * S * I;
-    double x[NX], u[NU], v[NU], xn[NX], F[NX];
+    double x[NX], u[NU], v[NU], xn[NX], F[NX], r[NX];
+    MMPC_UNROLL for (int a = 0; a < NX; ++a) r[a] = c.traj[(size_t)k * NX + a];  // with the other loads: one L2 round trip, not two
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         x[a] = fma(alpha, d[a * I], z[a * I]);
         xn[a] = fma(alpha, d[(S + a) * I], z[(S + a) * I]);
@@ -455,7 +456,7 @@ __device__ __forceinline__ void t3_trial_node(const T3Ctx<M, I, RK>& c, int k, d
     }
     c.template step<0>(x, u, nullptr, nullptr, nullptr, F, nullptr, nullptr, nullptr);
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
-        const double e = F[a] - c.traj[(size_t)k * NX + a];
+        const double e = F[a] - r[a];
         f1 = fma(c.Q[a] * e, e, f1);
         th1 += fabs(F[a] - xn[a]);
     }
@@ -521,6 +522,11 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I, C::RK>& cin, double
 #endif
         if (worker) {
             if (ch + 1 < nch) stage_chunk(ch + 1);
+            if (wj < C::CF && ch * C::CF + wj < N) {  // next step's merit evaluation: iterate rows and reference -> L1
+                const int kp = ch * C::CF + wj;
+                MMPC_UNROLL for (int a = 0; a < S + NX; ++a) t3_prefetch(c.V + ((size_t)kp * S + a) * I);
+                t3_prefetch(c.traj + (size_t)kp * NX);
+            }
             if (ch > 0) trial_chunk(ch - 1);
             cp_async_wait_all();
         } else if (tid < I) {
