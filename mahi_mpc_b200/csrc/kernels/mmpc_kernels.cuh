@@ -480,8 +480,8 @@ struct Launch {
     static cudaError_t mmpc_solve_dispatch_##MODEL(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io,  \
                                                    cudaStream_t st, int* launches) {                                    \
         if (P.integrator == MMPC_RK4 && P.is_linear) return cudaErrorNotSupported;                                      \
-        /* bounds: T1 only; RK4: T1, and T3 for small models (the ABI layer switches variants) */                        \
-        if ((W.variant == 2 || W.variant == 3) && P.bounded) return cudaErrorNotSupported;                              \
+        /* bounds and RK4: T1, and T3 for small models (the ABI layer switches variants) */                              \
+        if (W.variant == 2 && P.bounded) return cudaErrorNotSupported;                                                  \
         if (W.variant == 2 && P.integrator != MMPC_EULER) return cudaErrorNotSupported;                                 \
         if (launches) ++*launches;                                                                                      \
         if (W.variant == 2) return mmpc_solve_t2_##MODEL(&P, &W, &io, st);                                              \

@@ -37,8 +37,10 @@ struct T3 {
     __device__ static __forceinline__ int widx(int tid) { return tid - 32 - ((SK && tid >= 160) ? 32 : 0); }
     // Fx and Fu are stored compacted to their structural non-zeros (generator masks; dense if a mask does not fit 64 bits);
     // the value-function block Pxx is stored as its upper triangle
-    static constexpr int RK = RK_;  // RK4 shooting intervals: dense sensitivities (the one-step masks below hold for Euler / linearised steps only)
-    static constexpr bool SPARSE = !RK_ && NX * NX <= 64 && NX * NU <= 64;
+    // RK_ is a mode mask.  bit 0: RK4 shooting intervals -- dense sensitivities (the one-step masks below hold for Euler /
+    // linearised steps only); bit 1: finite bounds -- primal-dual interior point (T1's algorithm, mmpc_solve_t1.cuh)
+    static constexpr int RK = RK_ & 1, BD = (RK_ >> 1) & 1;
+    static constexpr bool SPARSE = !RK && NX * NX <= 64 && NX * NU <= 64;
     static constexpr unsigned long long fx_mask() {
         unsigned long long m = SPARSE ? M::A_MASK : ~0ULL;
         if (SPARSE) for (int i = 0; i < NX; ++i) m |= 1ULL << (i * NX + i);
@@ -54,17 +56,19 @@ struct T3 {
     static constexpr int NFX = SPARSE ? popc(FXM, NX * NX) : NX * NX, NFU = SPARSE ? popc(FUM, NX * NU) : NX * NU;
     static constexpr int NPX = NX * (NX + 1) / 2;
     // backward record fields (shared): Fx | Fu | H (packed full stage Hessian) | c | q~ = (qx, qv, qu)
-    static constexpr int RB_FX = 0, RB_FU = RB_FX + NFX, RB_H = RB_FU + NFU, RB_C = RB_H + NH, RB_Q = RB_C + NX, RB = RB_Q + N2;
+    // bounded: + Sigma and barrier gradient of x_{k+1} (they enter the value function of stage k+1)
+    static constexpr int RB_FX = 0, RB_FU = RB_FX + NFX, RB_H = RB_FU + NFU, RB_C = RB_H + NH, RB_Q = RB_C + NX, RB_SN = RB_Q + N2, RB_GN = RB_SN + NX,
+                         RB = RB_Q + N2 + (BD ? 2 * NX : 0);
     // global tile records per node
-    static constexpr int FG_FX = 0, FG_FU = NFX, FG_C = FG_FU + NFU, FG_Q = FG_C + NX, FG = FG_Q + N2;
+    static constexpr int FG_FX = 0, FG_FU = NFX, FG_C = FG_FU + NFU, FG_Q = FG_C + NX, FG_GN = FG_Q + N2, FG = FG_Q + N2 + (BD ? NX : 0);
     static constexpr int KG_KX = 0, KG_KV = NU * NX, KG_K0 = KG_KV + NU * NU, KG = KG_K0 + NU;
     static constexpr int PG_XX = 0, PG_XV = NPX, PG_X = PG_XV + NX * NU, PG = PG_X + NX;
     // forward record (shared) = FG | KG | PG
     static constexpr int RF_K = FG, RF_P = FG + KG, RF = FG + KG + PG;
     static constexpr int BUF = (CB * RB > CF * RF ? CB * RB : CF * RF) * I;  // one record buffer (two are used)
-    static constexpr int NRED = 5;           // per-(node,instance) reduction slots
+    static constexpr int NRED = BD ? 9 : 5;  // per-(node,instance) reduction slots
     static constexpr int REDBUF = NRED * CB * I;
-    static constexpr int SM_REC = 0, SM_RED = 2 * BUF, SM_INST = SM_RED + 2 * REDBUF, SM_END = SM_INST + 4 * I;
+    static constexpr int SM_REC = 0, SM_RED = 2 * BUF, SM_INST = SM_RED + 2 * REDBUF, SM_END = SM_INST + 6 * I;  // per instance: delta, alpha, flag, mu, alpha_z, spare
     static constexpr size_t SMEM_BYTES = sizeof(double) * SM_END;
     static constexpr int LIN = NX * NX + NX * NU + NX;
 };
@@ -110,6 +114,7 @@ struct T3Ctx {
     int N;
     double *V, *LAM, *DV, *LAMN;  // this thread's instance inside the tile arrays: element e lives at [e * I]
     double* LINp;                 // linearisation data of the instance (AoS)
+    double *ZL, *ZU, *DZL, *DZU;  // bounded: multipliers of the lower / upper bounds and their steps, in V layout like the iterate
     const double* traj;
     double Q[NX], R[NU], Rm[NU], uinit[NU];
     __device__ T3Ctx(const mmpc_problem& P_) : P(P_) {}
@@ -144,7 +149,7 @@ __device__ __forceinline__ void t3_prefetch_node(const T3Ctx<M, C::I, C::RK>& c,
 // ---- parallel phase of the backward sweep: thread (i, j) evaluates node k = k0 + j of instance i -------------
 // red slots: 0 dual_inf(max) 1 prim_inf(max) 2 theta 3 fval 4 lam_l1
 template <class M, class C>
-__device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I, C::RK>& c, int k, int i, int j, double delta, double* rec, double* red,
+__device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I, C::RK>& c, int k, int i, int j, double delta, double mu, double* rec, double* red,
                                              double* fg_tile) {
     constexpr int NX = M::NX, NU = M::NU, S = C::S, NH = C::NH, I = C::I;
     const int N = c.N;
@@ -164,6 +169,22 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I, C::RK>& c, int
         u_next[a] = (k < N - 1) ? z[(S + NX + a) * I] : 0.0;
     }
     MMPC_UNROLL for (int a = 0; a < NX; ++a) lam_prev[a] = k ? c.LAM[((size_t)(k - 1) * NX + a) * I] : 0.0;
+    // bounded: Sigma = z/s and the barrier gradient of u_k (stage Hessian / linear term) and of x_{k+1} (value function of
+    // stage k+1); the residual norms of the bounded problem come from t3_residuals, not from here
+    double sgu[NU], gpu_[NU], sgn[NX], gpn[NX];
+    if constexpr (C::BD) {
+        SweepNorms unused{};
+        const double* zl = c.ZL + (size_t)k * S * I;
+        const double* zu = c.ZU + (size_t)k * S * I;
+        MMPC_UNROLL for (int a = 0; a < NU; ++a) {
+            const BoundTerm t = bound_term(u[a], c.P.u_min[a], c.P.u_max[a], zl[(NX + a) * I], zu[(NX + a) * I], mu, unused);
+            sgu[a] = t.sigma; gpu_[a] = t.gphi;
+        }
+        MMPC_UNROLL for (int a = 0; a < NX; ++a) {
+            const BoundTerm t = bound_term(xn[a], c.P.x_min[a], c.P.x_max[a], zl[(S + a) * I], zu[(S + a) * I], mu, unused);
+            sgn[a] = t.sigma; gpn[a] = t.gphi;
+        }
+    }
     double F[NX], Fx[NX * NX], Fu[NX * NU], H[NH];
     c.template step<2>(x, u, wq, r, lam, F, Fx, Fu, H);
     double* const recp = rec + (size_t)j * C::RB * I + i;
@@ -201,11 +222,12 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I, C::RK>& c, int
             l = fma(Fu[q * NU + a], lam[q], l);
         }
         const double du = u[a] - v[a], dRu = 2.0 * c.R[a] * du;
-        const double qu = g + dRu + 2.0 * c.Rm[a] * u[a];
+        double qu = g + dRu + 2.0 * c.Rm[a] * u[a];
         const double dRn = (k < N - 1) ? 2.0 * c.R[a] * (u_next[a] - u[a]) : 0.0;
         fval = fma(c.R[a] * du, du, fval);
         fval = fma(c.Rm[a] * u[a], u[a], fval);
         dual = fmax(dual, fabs(qu + l - dRn));
+        if constexpr (C::BD != 0) { qu += gpu_[a]; }
         T3_REC(C::RB_Q + NX + a) = -dRu;  T3_FG(C::FG_Q + NX + a, -dRu);
         T3_REC(C::RB_Q + S + a) = qu;     T3_FG(C::FG_Q + S + a, qu);
     }
@@ -220,7 +242,17 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I, C::RK>& c, int
             }
         }
         if (p == d) acc += delta + (p >= NX ? 2.0 * (c.R[p - NX] + c.Rm[p - NX]) : 0.0);
+        if constexpr (C::BD != 0) {
+            if (p == d && p >= NX) acc += sgu[p - NX];
+        }
         T3_REC(C::RB_H + tri(p, d, S)) = acc;
+    }
+    if constexpr (C::BD != 0) {
+        MMPC_UNROLL for (int a = 0; a < NX; ++a) {
+            T3_REC(C::RB_SN + a) = sgn[a];
+            T3_REC(C::RB_GN + a) = gpn[a];
+            T3_FG(C::FG_GN + a, gpn[a]);
+        }
     }
 #undef T3_REC
 #undef T3_FG
@@ -247,6 +279,15 @@ __device__ __forceinline__ bool t3_riccati_stage(T3Riccati<M>& V, const double* 
     MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) Fx[a] = T3_FXNZ(a / NX, a % NX) ? T3_R(C::RB_FX + T3_FXSLOT(a)) : 0.0;
     MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) Fu[a] = T3_FUNZ(a / NU, a % NU) ? T3_R(C::RB_FU + T3_FUSLOT(a)) : 0.0;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) cres[a] = T3_R(C::RB_C + a);
+    // NOTE: keep `#pragma unroll` loops of an `if constexpr` branch inside braces.  With nvcc 12.9 the form
+    // `if constexpr (C::BD) _Pragma("unroll") for (...) {...}` changed the multipliers this function's callers computed in the
+    // instantiations where the branch is discarded (one more Newton iteration per solve; tools/it_cmp.py shows it).
+    if constexpr (C::BD != 0) {  // barrier of x_{k+1}: part of the value function of stage k+1
+        MMPC_UNROLL for (int a = 0; a < NX; ++a) {
+            V.Pxx[a * NX + a] += T3_R(C::RB_SN + a);
+            V.px[a] += T3_R(C::RB_GN + a);
+        }
+    }
     // value function of stage k+1 -> global (the forward sweep needs it for lam_k)
     MMPC_UNROLL for (int a = 0; a < NX; ++a) MMPC_UNROLL for (int b = a; b < NX; ++b) T3_ST(&pg[(C::PG_XX + tri(a, b, NX)) * I], V.Pxx[a * NX + b]);
     MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) T3_ST(&pg[(C::PG_XV + a) * I], V.Pxv[a]);
@@ -382,6 +423,7 @@ __device__ __noinline__ bool t3_backward(const T3Ctx<M, C::I, C::RK>& cin, doubl
     // recursion, which is worth ~70 registers to each side.
     if (worker) {
         const double delta = dl[wi];
+        const double mu = C::BD ? smem[C::SM_INST + 3 * I + wi] : 0.0;  // barrier parameter of the instance (bounded problems)
         for (int step = nch; step >= 0; --step) {
 #ifdef MMPC_T3_PROFILE_SWEEPS
             const long long t0 = clock64();
@@ -390,7 +432,7 @@ __device__ __noinline__ bool t3_backward(const T3Ctx<M, C::I, C::RK>& cin, doubl
             if (ch >= 0) {
                 const int k0 = (int)((long long)ch * N / nch), kn = (int)((long long)(ch + 1) * N / nch) - k0;  // balanced chunks (<= CB nodes)
                 if (ch > 0 && wj < k0 - (int)((long long)(ch - 1) * N / nch)) t3_prefetch_node<M, C>(c, (int)((long long)(ch - 1) * N / nch) + wj);
-                if (wj < kn) t3_eval_node<M, C>(c, k0 + wj, wi, wj, delta, smem + C::SM_REC + (ch & 1) * C::BUF, smem + C::SM_RED + (ch & 1) * C::REDBUF, fg_tile);
+                if (wj < kn) t3_eval_node<M, C>(c, k0 + wj, wi, wj, delta, mu, smem + C::SM_REC + (ch & 1) * C::BUF, smem + C::SM_RED + (ch & 1) * C::REDBUF, fg_tile);
             }
 #ifdef MMPC_T3_PROFILE_SWEEPS
             t_work += clock64() - t0;
@@ -438,10 +480,114 @@ __device__ __noinline__ bool t3_backward(const T3Ctx<M, C::I, C::RK>& cin, doubl
     return ok;
 }
 
+// ---- bounded problems: KKT residuals of the current iterate (T1's backward_sweep<RICCATI = false>): the barrier parameter
+// is chosen from them BEFORE the Riccati sweep, so they get their own pass.  Workers only, node k of instance i per thread;
+// no second derivatives.  Slots: 0 dual_inf 1 prim_inf 2 theta 3 fval 4 lam_l1 5 z_l1 6 max s*z 7 min s*z 8 -sum log s
+struct T3NormsBD {
+    double dual_inf, prim_inf, theta, fval, lam_l1, z_l1, cmax, cmin, barrier;
+};
+template <class M, class C>
+__device__ __noinline__ void t3_residuals(const T3Ctx<M, C::I, C::RK>& cin, double* smem, int tid, T3NormsBD& out) {
+    constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
+    const T3Ctx<M, C::I, C::RK> c = cin;
+    const int N = c.N;
+    const bool worker = C::is_worker(tid);
+    const int w = C::widx(tid), wi = w % I, wj = w / I;
+    double* red = smem + C::SM_RED;
+    if (worker) {
+        SweepNorms n;
+        n.dual_inf = n.prim_inf = n.theta = n.fval = n.lam_l1 = n.z_l1 = n.cmax = n.barrier = 0.0;
+        n.cmin = INFINITY;
+        for (int k = wj; k < N; k += C::CB) {
+            const double* z = c.V + (size_t)k * S * I;
+            const double* zl = c.ZL + (size_t)k * S * I;
+            const double* zu = c.ZU + (size_t)k * S * I;
+            double x[NX], u[NU], v[NU], r[NX], lam[NX], xn[NX], lam_prev[NX], u_next[NU];
+            double zlx[NX], zux[NX], zlu[NU], zuu[NU], zln[NX], zun[NX];
+            MMPC_UNROLL for (int a = 0; a < NX; ++a) {
+                x[a] = z[a * I];
+                xn[a] = z[(S + a) * I];
+                r[a] = c.traj[(size_t)k * NX + a];
+                lam[a] = c.LAM[((size_t)k * NX + a) * I];
+                lam_prev[a] = k ? c.LAM[((size_t)(k - 1) * NX + a) * I] : 0.0;
+                zlx[a] = k ? zl[a * I] : 0.0; zux[a] = k ? zu[a * I] : 0.0;
+                zln[a] = zl[(S + a) * I]; zun[a] = zu[(S + a) * I];
+            }
+            MMPC_UNROLL for (int a = 0; a < NU; ++a) {
+                u[a] = z[(NX + a) * I];
+                v[a] = k ? z[(NX + a - S) * I] : c.uinit[a];
+                u_next[a] = (k < N - 1) ? z[(S + NX + a) * I] : 0.0;
+                zlu[a] = zl[(NX + a) * I]; zuu[a] = zu[(NX + a) * I];
+            }
+            double F[NX], Fx[NX * NX], Fu[NX * NU], qe[NX];
+            c.template step<1>(x, u, nullptr, nullptr, nullptr, F, Fx, Fu, nullptr);
+            SweepNorms own{};  // x_k's terms are accumulated by node k-1 (as its x_{k+1}); here only its -zl + zu is needed
+            MMPC_UNROLL for (int a = 0; a < NX; ++a) {
+                const double e = F[a] - r[a], cr = F[a] - xn[a];
+                qe[a] = 2.0 * c.Q[a] * e;
+                n.fval = fma(c.Q[a] * e, e, n.fval);
+                n.prim_inf = fmax(n.prim_inf, fabs(cr));
+                n.theta += fabs(cr);
+                n.lam_l1 += fabs(lam[a]);
+                const BoundTerm tn = bound_term(xn[a], c.P.x_min[a], c.P.x_max[a], zln[a], zun[a], 0.0, n);
+                if (k == N - 1) n.dual_inf = fmax(n.dual_inf, fabs(-lam[a] + tn.dres));  // stationarity w.r.t. x_N
+            }
+            MMPC_UNROLL for (int a = 0; a < NX; ++a) {
+                double g = 0.0, l = 0.0;
+                MMPC_UNROLL for (int q = 0; q < NX; ++q) {
+                    g = fma(Fx[q * NX + a], qe[q], g);
+                    l = fma(Fx[q * NX + a], lam[q], l);
+                }
+                if (k) {
+                    const BoundTerm tx = bound_term(x[a], c.P.x_min[a], c.P.x_max[a], zlx[a], zux[a], 0.0, own);
+                    n.dual_inf = fmax(n.dual_inf, fabs(g + l - lam_prev[a] + tx.dres));
+                }
+            }
+            MMPC_UNROLL for (int a = 0; a < NU; ++a) {
+                double g = 0.0, l = 0.0;
+                MMPC_UNROLL for (int q = 0; q < NX; ++q) {
+                    g = fma(Fu[q * NU + a], qe[q], g);
+                    l = fma(Fu[q * NU + a], lam[q], l);
+                }
+                const double du = u[a] - v[a], dRu = 2.0 * c.R[a] * du;
+                const double dRn = (k < N - 1) ? 2.0 * c.R[a] * (u_next[a] - u[a]) : 0.0;
+                n.fval = fma(c.R[a] * du, du, n.fval);
+                n.fval = fma(c.Rm[a] * u[a], u[a], n.fval);
+                const BoundTerm tu = bound_term(u[a], c.P.u_min[a], c.P.u_max[a], zlu[a], zuu[a], 0.0, n);
+                n.dual_inf = fmax(n.dual_inf, fabs(g + dRu + 2.0 * c.Rm[a] * u[a] + l - dRn + tu.dres));
+            }
+        }
+        red[(0 * C::CB + wj) * I + wi] = n.dual_inf; red[(1 * C::CB + wj) * I + wi] = n.prim_inf;
+        red[(2 * C::CB + wj) * I + wi] = n.theta;    red[(3 * C::CB + wj) * I + wi] = n.fval;
+        red[(4 * C::CB + wj) * I + wi] = n.lam_l1;   red[(5 * C::CB + wj) * I + wi] = n.z_l1;
+        red[(6 * C::CB + wj) * I + wi] = n.cmax;     red[(7 * C::CB + wj) * I + wi] = n.cmin;
+        red[(8 * C::CB + wj) * I + wi] = n.barrier;
+    }
+    __syncthreads();
+    T3NormsBD o;
+    o.dual_inf = o.prim_inf = o.theta = o.fval = o.lam_l1 = o.z_l1 = o.cmax = o.barrier = 0.0;
+    o.cmin = INFINITY;
+    if (tid < I) MMPC_UNROLL for (int s = 0; s < C::CB; ++s) {
+        o.dual_inf = fmax(o.dual_inf, red[(0 * C::CB + s) * I + tid]); o.prim_inf = fmax(o.prim_inf, red[(1 * C::CB + s) * I + tid]);
+        o.theta += red[(2 * C::CB + s) * I + tid];                      o.fval += red[(3 * C::CB + s) * I + tid];
+        o.lam_l1 += red[(4 * C::CB + s) * I + tid];                     o.z_l1 += red[(5 * C::CB + s) * I + tid];
+        o.cmax = fmax(o.cmax, red[(6 * C::CB + s) * I + tid]);          o.cmin = fmin(o.cmin, red[(7 * C::CB + s) * I + tid]);
+        o.barrier += red[(8 * C::CB + s) * I + tid];
+    }
+    __syncthreads();
+    out = o;
+}
+
 // merit pieces of node k at z + alpha dz
-template <class M, int I, int RK>
-__device__ __forceinline__ void t3_trial_node(const T3Ctx<M, I, RK>& c, int k, double alpha, double& f1, double& th1) {
-    constexpr int NX = M::NX, NU = M::NU, S = NX + NU;
+// bounded problems: barrier of the trial point and, for the full step of the forward sweep (full = true), the multiplier
+// steps and the fraction-to-the-boundary limits (T1's bound_step)
+struct T3TrialBD {
+    double bar1, amax, az, mu, tau;
+    bool full;
+};
+template <class M, class C>
+__device__ __forceinline__ void t3_trial_node(const T3Ctx<M, C::I, C::RK>& c, int k, double alpha, double& f1, double& th1, T3TrialBD& bd) {
+    constexpr int NX = M::NX, NU = M::NU, S = NX + NU, I = C::I;
     const double* z = c.V + (size_t)k * S * I;
     const double* d = c.DV + (size_t)k * S * I;
     double x[NX], u[NU], v[NU], xn[NX], F[NX], r[NX];
@@ -465,10 +611,35 @@ __device__ __forceinline__ void t3_trial_node(const T3Ctx<M, I, RK>& c, int k, d
         f1 = fma(c.R[a] * dd, dd, f1);
         f1 = fma(c.Rm[a] * u[a], u[a], f1);
     }
+    if constexpr (C::BD) {
+        if (bd.full) {  // alpha = 1: u, xn are z + dz; bound_step wants the iterate and the step
+            FwdOut o;
+            o.amax = bd.amax; o.az = bd.az; o.bar1 = bd.bar1;
+            const double* zl = c.ZL + (size_t)k * S * I;
+            const double* zu = c.ZU + (size_t)k * S * I;
+            double* dzl = c.DZL + (size_t)k * S * I;
+            double* dzu = c.DZU + (size_t)k * S * I;
+            MMPC_UNROLL for (int a = 0; a < NU; ++a) {
+                double dl, du_;
+                bound_step(z[(NX + a) * I], d[(NX + a) * I], c.P.u_min[a], c.P.u_max[a], zl[(NX + a) * I], zu[(NX + a) * I], bd.mu, bd.tau, dl, du_, o);
+                dzl[(NX + a) * I] = dl; dzu[(NX + a) * I] = du_;
+            }
+            MMPC_UNROLL for (int a = 0; a < NX; ++a) {
+                double dl, du_;
+                bound_step(z[(S + a) * I], d[(S + a) * I], c.P.x_min[a], c.P.x_max[a], zl[(S + a) * I], zu[(S + a) * I], bd.mu, bd.tau, dl, du_, o);
+                dzl[(S + a) * I] = dl; dzu[(S + a) * I] = du_;
+            }
+            bd.amax = o.amax; bd.az = o.az; bd.bar1 = o.bar1;
+        } else {
+            MMPC_UNROLL for (int a = 0; a < NU; ++a) bd.bar1 += barrier_of(u[a], c.P.u_min[a], c.P.u_max[a]);
+            MMPC_UNROLL for (int a = 0; a < NX; ++a) bd.bar1 += barrier_of(xn[a], c.P.x_min[a], c.P.x_max[a]);
+        }
+    }
 }
 
 struct T3Fwd {
     double gradf_d, lam_inf, f1, th1;
+    double bar1, amax, az;  // bounded problems: barrier at the full step, step-length limits of the primal and the bound multipliers
     bool finite;
 };
 
@@ -487,7 +658,8 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I, C::RK>& cin, double
     double dx[NX], dv[NU];
     MMPC_UNROLL for (int a = 0; a < NX; ++a) dx[a] = 0.0;
     MMPC_UNROLL for (int a = 0; a < NU; ++a) dv[a] = 0.0;
-    o.gradf_d = o.lam_inf = o.f1 = o.th1 = 0.0;
+    o.gradf_d = o.lam_inf = o.f1 = o.th1 = o.bar1 = 0.0;
+    o.amax = o.az = 1.0;
     o.finite = true;
     const int nch = (N + C::CF - 1) / C::CF;
     auto stage_chunk = [&](int ch) {  // [node][field][instance] blocks are contiguous in the tile arrays
@@ -504,9 +676,13 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I, C::RK>& cin, double
         }
     };
     double f1 = 0.0, th1 = 0.0;  // worker-local merit sums
+    T3TrialBD bd;
+    bd.bar1 = 0.0; bd.amax = bd.az = 1.0; bd.full = true;
+    bd.mu = C::BD ? smem[C::SM_INST + 3 * I + (worker ? wi : 0)] : 0.0;
+    bd.tau = fmax(0.99, 1.0 - bd.mu);  // IPOPT tau_min = 0.99 [upstream]
     auto trial_chunk = [&](int ch) {  // workers with node slot < CF take part
         const int k0 = ch * C::CF, kn = min(C::CF, N - k0);
-        if (wj < kn) t3_trial_node<M, I, C::RK>(c, k0 + wj, 1.0, f1, th1);
+        if (wj < kn) t3_trial_node<M, C>(c, k0 + wj, 1.0, f1, th1, bd);
     };
 #ifdef MMPC_T3_PROFILE_SWEEPS
     long long t_work = 0, t_all0 = clock64();
@@ -555,6 +731,9 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I, C::RK>& cin, double
                     o.gradf_d = fma(T3_F(C::FG_Q + NX + a), dv[a], o.gradf_d);
                     o.gradf_d = fma(T3_F(C::FG_Q + S + a), du[a], o.gradf_d);
                 }
+                if constexpr (C::BD != 0) {  // barrier gradient of x_{k+1} . dx_{k+1}
+                    MMPC_UNROLL for (int a = 0; a < NX; ++a) o.gradf_d = fma(T3_F(C::FG_GN + a), dxn[a], o.gradf_d);
+                }
                 MMPC_UNROLL for (int a = 0; a < NX; ++a) {
                     double t = T3_F(C::RF_P + C::PG_X + a);
                     MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(T3_F(C::RF_P + C::PG_XX + trisym(a, q, NX)), dxn[q], t);
@@ -583,11 +762,21 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I, C::RK>& cin, double
         trial_chunk(nch - 1);
         red[(0 * C::CB + wj) * I + wi] = f1;
         red[(1 * C::CB + wj) * I + wi] = th1;
+        if constexpr (C::BD) {
+            red[(2 * C::CB + wj) * I + wi] = bd.bar1;
+            red[(3 * C::CB + wj) * I + wi] = bd.amax;
+            red[(4 * C::CB + wj) * I + wi] = bd.az;
+        }
     }
     __syncthreads();
     if (tid < I) MMPC_UNROLL for (int s = 0; s < C::CF; ++s) {
         o.f1 += red[(0 * C::CB + s) * I + tid];
         o.th1 += red[(1 * C::CB + s) * I + tid];
+        if constexpr (C::BD) {
+            o.bar1 += red[(2 * C::CB + s) * I + tid];
+            o.amax = fmin(o.amax, red[(3 * C::CB + s) * I + tid]);
+            o.az = fmin(o.az, red[(4 * C::CB + s) * I + tid]);
+        }
     }
     __syncthreads();
     o_out = o;
@@ -595,7 +784,7 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I, C::RK>& cin, double
 
 // merit of z + alpha_i dz for every instance of the tile (alpha per instance in shared memory)
 template <class M, class C>
-__device__ __noinline__ void t3_trial(const T3Ctx<M, C::I, C::RK>& cin, double* smem, int tid, double& f1, double& th1) {
+__device__ __noinline__ void t3_trial(const T3Ctx<M, C::I, C::RK>& cin, double* smem, int tid, double& f1, double& th1, double& bar1) {
     constexpr int I = C::I;
     const T3Ctx<M, C::I, C::RK> c = cin;
     const bool worker = C::is_worker(tid);
@@ -604,15 +793,19 @@ __device__ __noinline__ void t3_trial(const T3Ctx<M, C::I, C::RK>& cin, double* 
     if (worker) {
         const double alpha = smem[C::SM_INST + I + wi];
         double a1 = 0.0, a2 = 0.0;
-        for (int k = wj; k < c.N; k += C::CB) t3_trial_node<M, I, C::RK>(c, k, alpha, a1, a2);
+        T3TrialBD bd;
+        bd.bar1 = 0.0; bd.amax = bd.az = 1.0; bd.mu = bd.tau = 0.0; bd.full = false;
+        for (int k = wj; k < c.N; k += C::CB) t3_trial_node<M, C>(c, k, alpha, a1, a2, bd);
         red[(0 * C::CB + wj) * I + wi] = a1;
         red[(1 * C::CB + wj) * I + wi] = a2;
+        if constexpr (C::BD) red[(2 * C::CB + wj) * I + wi] = bd.bar1;
     }
     __syncthreads();
-    f1 = 0.0; th1 = 0.0;
+    f1 = 0.0; th1 = 0.0; bar1 = 0.0;
     if (tid < I) MMPC_UNROLL for (int s = 0; s < C::CB; ++s) {
         f1 += red[(0 * C::CB + s) * I + tid];
         th1 += red[(1 * C::CB + s) * I + tid];
+        if constexpr (C::BD) bar1 += red[(2 * C::CB + s) * I + tid];
     }
     __syncthreads();
 }
@@ -642,6 +835,8 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
     c.V = W.V2 + (size_t)tile * I * NV + i; c.LAM = W.LAM2 + (size_t)tile * I * Mc + i;
     c.DV = W.DV2 + (size_t)tile * I * NV + i; c.LAMN = W.LAMN2 + (size_t)tile * I * Mc + i;
     c.LINp = W.LIN2 + (size_t)b * C::LIN;
+    c.ZL = W.ZL2 + (size_t)tile * I * NV + i; c.ZU = W.ZU2 + (size_t)tile * I * NV + i;
+    c.DZL = W.DZL2 + (size_t)tile * I * NV + i; c.DZU = W.DZU2 + (size_t)tile * I * NV + i;
     c.traj = io.traj + (size_t)bi * N * NX;
     double* fg_tile = W.FG2 + (size_t)tile * I * N * C::FG;
     double* kg_tile = W.KG2 + (size_t)tile * I * N * C::KG;
@@ -660,6 +855,20 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
         for (int e = j; e < NX; e += C::CB) {
             c.V[(size_t)e * I] = io.state[(size_t)bi * NX + e];
             c.DV[(size_t)e * I] = 0.0;
+        }
+    }
+    if constexpr (C::BD) {
+        // push the start into the interior (IPOPT bound_push = bound_frac = 1e-2) and set z = 1 [upstream]; x_0 is pinned
+        if (worker) for (int e = NX + j; e < NV; e += C::CB) {
+            const int r = e % S;
+            const double lb = r < NX ? P.x_min[r] : P.u_min[r - NX], ub = r < NX ? P.x_max[r] : P.u_max[r - NX];
+            const bool hl = lb > -MMPC_INF_THRESH, hu = ub < MMPC_INF_THRESH;
+            double v = c.V[(size_t)e * I];
+            if (hl) { double p = 1e-2 * fmax(1.0, fabs(lb)); if (hu) p = fmin(p, 1e-2 * (ub - lb)); v = fmax(v, lb + p); }
+            if (hu) { double p = 1e-2 * fmax(1.0, fabs(ub)); if (hl) p = fmin(p, 1e-2 * (ub - lb)); v = fmin(v, ub - p); }
+            c.V[(size_t)e * I] = v;
+            c.ZL[(size_t)e * I] = hl ? 1.0 : 0.0;
+            c.ZU[(size_t)e * I] = hu ? 1.0 : 0.0;
         }
     }
     __syncthreads();
@@ -686,13 +895,45 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
 #ifdef MMPC_T3_PROFILE
     const long long t_kernel0 = clock64();
 #endif
+    double mu = C::BD ? io.mu_init : 0.0, barrier0 = 0.0;
+    double* sh_mu = smem + C::SM_INST + 3 * I;  // per-instance barrier parameter
+    double* sh_az = smem + C::SM_INST + 4 * I;  // per-instance step length of the bound multipliers
     for (it = 0;; ++it) {
         T3Norms nrm;
         double delta = 0.0;
+        bool ok = true;
+        if constexpr (C::BD) {
+            // residuals first: the barrier parameter is chosen from them (T1's bounded iteration, mmpc_solve_t1.cuh)
+            T3NormsBD nb;
+            t3_residuals<M, C>(c, smem, tid, nb);
+            nrm.dual_inf = nb.dual_inf; nrm.prim_inf = nb.prim_inf; nrm.theta = nb.theta; nrm.fval = nb.fval; nrm.lam_l1 = nb.lam_l1;
+            barrier0 = nb.barrier;
+            if (active) {
+                // IPOPT scaled optimality error (Waechter & Biegler 2006 eq. 5-6) [upstream]: s_max = 100
+                const double sd = fmax(100.0, (nb.lam_l1 + nb.z_l1) / (double)(nfree + ncon)) / 100.0;
+                const double sc = fmax(100.0, nb.z_l1 / (double)nfree) / 100.0;
+                const double e_dp = fmax(nb.dual_inf / sd, nb.prim_inf);
+                err = fmax(e_dp, nb.cmax / sc);
+                fval = nb.fval;
+                it_done = it;
+                if (!isfinite(err)) { status = MMPC_SOLVE_NUMERICAL; active = false; }
+                else if (err <= io.tol) { status = MMPC_SOLVE_CONVERGED; active = false; }
+                else if (it >= io.max_iter) { status = MMPC_SOLVE_MAX_ITER; active = false; }
+                else {
+                    // monotone barrier update (kappa_eps = 10, kappa_mu = 0.2, theta_mu = 1.5) [upstream]
+                    while (mu > io.tol / 10.0 && fmax(e_dp, fmax(nb.cmax - mu, mu - nb.cmin) / sc) <= 10.0 * mu)
+                        mu = fmax(io.tol / 10.0, fmin(0.2 * mu, mu * sqrt(mu)));
+                }
+            }
+            if (tid < I) sh_mu[tid] = mu;
+            if (!__syncthreads_or(active)) break;
+            T3Norms unused;
+            ok = t3_backward<M, C>(c, smem, tid, delta, unused, fg_tile, kg_tile, pg_tile);
+        } else {
 #ifdef MMPC_T3_PROFILE
         const long long tp0 = clock64();
 #endif
-        bool ok = t3_backward<M, C>(c, smem, tid, delta, nrm, fg_tile, kg_tile, pg_tile);
+        ok = t3_backward<M, C>(c, smem, tid, delta, nrm, fg_tile, kg_tile, pg_tile);
 #ifdef MMPC_T3_PROFILE
         if (it < 8) t_bwd[it] = clock64() - tp0;
 #endif
@@ -704,6 +945,7 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
             if (!isfinite(err)) { status = MMPC_SOLVE_NUMERICAL; active = false; }
             else if (err <= io.tol) { status = MMPC_SOLVE_CONVERGED; active = false; }
             else if (it >= io.max_iter) { status = MMPC_SOLVE_MAX_ITER; active = false; }
+        }
         }
         if (!__syncthreads_or(active)) break;
         int tries = 0;
@@ -733,22 +975,31 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
 #endif
         if (active && !(fo.finite && isfinite(fo.f1))) { status = MMPC_SOLVE_NUMERICAL; active = false; }
         nu_merit = fmax(nu_merit, 1.1 * fo.lam_inf + 1e-8);
-        const double m0 = nrm.fval + nu_merit * nrm.theta;
+        const double m0 = nrm.fval + mu * barrier0 + nu_merit * nrm.theta;  // mu = 0 without bounds
         const double D = fo.gradf_d - nu_merit * nrm.theta;
-        double alpha = 1.0;
+        double alpha = C::BD ? fo.amax : 1.0;  // fraction to the boundary
+        double f1 = fo.f1, th1 = fo.th1, bar1 = fo.bar1;
         int ls = 0;
-        bool need = active && !(fo.f1 + nu_merit * fo.th1 <= m0 + 1e-4 * alpha * D + 1e-12 * fabs(m0));
+        if constexpr (C::BD) {
+            if (__syncthreads_or(active && alpha < 1.0)) {  // the merit terms of the forward sweep are those of alpha = 1
+                if (tid < I) sh_alpha[tid] = alpha;
+                __syncthreads();
+                t3_trial<M, C>(c, smem, tid, f1, th1, bar1);
+            }
+        }
+        bool need = active && !(f1 + mu * bar1 + nu_merit * th1 <= m0 + 1e-4 * alpha * D + 1e-12 * fabs(m0));
         while (__syncthreads_or(need)) {
             if (need) { alpha *= 0.5; ++ls_total; }
             if (tid < I) sh_alpha[tid] = alpha;
             __syncthreads();
-            double f2, t2;
-            t3_trial<M, C>(c, smem, tid, f2, t2);
-            if (need) need = !(f2 + nu_merit * t2 <= m0 + 1e-4 * alpha * D + 1e-12 * fabs(m0)) && (++ls < 40);
+            double f2, t2, b2;
+            t3_trial<M, C>(c, smem, tid, f2, t2, b2);
+            if (need) need = !(f2 + mu * b2 + nu_merit * t2 <= m0 + 1e-4 * alpha * D + 1e-12 * fabs(m0)) && (++ls < 40);
         }
         if (tid < I) {
             sh_alpha[tid] = alpha;
             sh_flag[tid] = active ? 1.0 : 0.0;
+            if constexpr (C::BD) sh_az[tid] = fo.az;
         }
         __syncthreads();
         if (worker && sh_flag[i] != 0.0) {  // the C workers of an instance update its iterate together, loads batched
@@ -763,6 +1014,17 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
                 double vl[UB], vn[UB];
                 MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) { vl[q] = LAMp[(size_t)(e0 + q * C::CB) * I]; vn[q] = LAMNp[(size_t)(e0 + q * C::CB) * I]; }
                 MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) LAMp[(size_t)(e0 + q * C::CB) * I] = fma(al, vn[q] - vl[q], vl[q]);
+            }
+            if constexpr (C::BD) {
+                // bound multipliers: z += alpha_z dz, then IPOPT's kappa_sigma safeguard at the new point (T1)
+                const double az = sh_az[i], mu_i = sh_mu[i];
+                for (int e = NX + j; e < NV; e += C::CB) {
+                    const int r = e % S;
+                    const double lb = r < NX ? P.x_min[r] : P.u_min[r - NX], ub = r < NX ? P.x_max[r] : P.u_max[r - NX];
+                    const double v = Vp[(size_t)e * I];  // the updated value (this thread wrote it above)
+                    if (lb > -MMPC_INF_THRESH) c.ZL[(size_t)e * I] = z_safeguard(fma(az, c.DZL[(size_t)e * I], c.ZL[(size_t)e * I]), v - lb, mu_i);
+                    if (ub < MMPC_INF_THRESH) c.ZU[(size_t)e * I] = z_safeguard(fma(az, c.DZU[(size_t)e * I], c.ZU[(size_t)e * I]), ub - v, mu_i);
+                }
             }
         }
         __syncthreads();
@@ -790,7 +1052,7 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
     }
     if (valid && tid < I && io.stats) {
         mmpc_stats s;
-        s.objective = fval; s.kkt_error = err; s.mu = 0.0; s.iterations = it_done; s.status = status;
+        s.objective = fval; s.kkt_error = err; s.mu = mu; s.iterations = it_done; s.status = status;
         s.ls_steps = ls_total; s.reg_steps = reg_total;
         io.stats[b] = s;
     }
@@ -830,6 +1092,16 @@ struct LaunchT3 {
     static cudaError_t run(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         const int forced = io.variant >> 8;
         const int cfg = forced ? forced : (W.B > 2 * 8 * 148 ? 2 : 1);
+        if (P.bounded) {
+            // finite bounds: interior point (Euler / linearised steps; bounded RK4 solves stay on T1); small models only
+            if constexpr (M::NX + 2 * M::NU <= 8) {
+                if (P.integrator == MMPC_RK4 && !P.is_linear) return cudaErrorNotSupported;
+                if (cfg == 2) return go<32, 6, 5, 0, 2>(P, W, io, st);
+                return go<8, 4, 4, 0, 2>(P, W, io, st);
+            } else {
+                return cudaErrorNotSupported;
+            }
+        }
         if (P.integrator == MMPC_RK4 && !P.is_linear) {
             // RK4 shooting (dense sensitivities, Gauss-Newton Hessian); instantiated for the small models T3 is the default for
             if constexpr (M::NX + 2 * M::NU <= 8) {

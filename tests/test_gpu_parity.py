@@ -265,7 +265,12 @@ def test_solve_per_instance_weights_and_errors(api):
         api.Model("no_such_model", N=5, nx=3, nu=1)
 
 
-def test_bounded_solve_vs_golden(api, golden):
+# interior point: T1 (thread per instance), the default (T3 for the pendulum) and T3's 32-instance tile configuration
+BOUNDED_VARIANTS = [1, 0, 3 + 256 * 2]
+
+
+@pytest.mark.parametrize("variant", BOUNDED_VARIANTS)
+def test_bounded_solve_vs_golden(api, golden, variant):
     """Finite control limits (ModelControl::update_control_limits, ModelControl.cpp:205-209): interior-point path."""
     gs = golden["solves"]
     n = 0
@@ -277,7 +282,7 @@ def test_bounded_solve_vs_golden(api, golden):
         P = nlp.Problem(N=N)
         pv = P.split_p(np.array(case["p"]))
         m = api.Model("double_pendulum", N=N)
-        s = api.Solver(m, 1, tol=1e-9)
+        s = api.Solver(m, 1, tol=1e-9, kernel_variant=variant)
         s.set_weights(pv["Q"], pv["R"], pv["Rm"])
         s.set_bounds(u_min=[-ub, -ub], u_max=[ub, ub])
         V, lam, st = s.solve(np.array(case["x0"])[None], pv["u_init"][None].copy(), pv["r"][None].copy())
@@ -290,14 +295,15 @@ def test_bounded_solve_vs_golden(api, golden):
     assert n == 2
 
 
+@pytest.mark.parametrize("variant", BOUNDED_VARIANTS)
 @pytest.mark.parametrize("N,B,ub,xb", [(25, 16, 2.5, None), (50, 40, 1.5, None), (25, 8, 4.0, 0.9)])
-def test_bounded_solve_vs_oracle(api, coracle, N, B, ub, xb):
+def test_bounded_solve_vs_oracle(api, coracle, N, B, ub, xb, variant):
     P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B, seed_offset=300)
     x_min = x_max = None
     if xb is not None:  # also a state bound on the first joint velocity-like state
         x_min, x_max = [-NB, -NB, -NB, -NB], [xb, NB, NB, NB]
     m = api.Model("double_pendulum", N=N, u_min=[-ub, -ub], u_max=[ub, ub], x_min=x_min, x_max=x_max)
-    s = api.Solver(m, B, tol=1e-10)  # same barrier end point (mu = tol/10) on both sides
+    s = api.Solver(m, B, tol=1e-10, kernel_variant=variant)  # same barrier end point (mu = tol/10) on both sides
     s.set_weights(Q, R, Rm)
     V, lam, st = s.solve(x0, up, traj)
     lb, ubv = nlp.bounds_vectors(P, x0[0], x_min=x_min, x_max=x_max, u_min=[-ub] * 2, u_max=[ub] * 2)
@@ -312,7 +318,7 @@ def test_bounded_solve_vs_oracle(api, coracle, N, B, ub, xb):
         assert V[:, 6::6][:, :N].max() <= xb + 1e-12
     # unbounded handle switched to bounds later (update_control_limits) gives the same answer
     m2 = api.Model("double_pendulum", N=N)
-    s2 = api.Solver(m2, B, tol=1e-10)
+    s2 = api.Solver(m2, B, tol=1e-10, kernel_variant=variant)
     s2.set_weights(Q, R, Rm)
     s2.solve(x0, up, traj)
     s2.set_bounds(x_min=x_min, x_max=x_max, u_min=[-ub, -ub], u_max=[ub, ub])

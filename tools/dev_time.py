@@ -10,7 +10,10 @@ for B in [int(v) for v in sys.argv[3:]]:
     Q, R, Rm = workload.default_weights(4, 2)
     m = api.Model("double_pendulum", N=N); rk = int(os.environ.get("MMPC_RK4", "0"))
     kw = dict(integrator=api.RK4, substeps=rk) if rk else {}
-    s = api.Solver(m, B, warm_start=0, kernel_variant=variant, **kw); s.set_weights(Q, R, Rm)
+    s = api.Solver(m, B, warm_start=0, kernel_variant=variant, **kw)
+    if os.environ.get("MMPC_UBOUND"):
+        ub = float(os.environ["MMPC_UBOUND"]); s.set_bounds(u_min=[-ub, -ub], u_max=[ub, ub])
+    s.set_weights(Q, R, Rm)
     d = [torch.from_numpy(a).to(dev) for a in (x0, up, traj)]
     V = torch.empty(B, m.NV, dtype=torch.float64, device=dev); st = torch.empty(B, 5, dtype=torch.float64, device=dev)
     for _ in range(3): s.solve(*d, V_out=V, stats_out=st, want_lam=False)
