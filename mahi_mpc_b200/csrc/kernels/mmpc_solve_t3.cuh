@@ -39,7 +39,7 @@ struct T3 {
     // the value-function block Pxx is stored as its upper triangle
     // RK_ is a mode mask.  bit 0: RK4 shooting intervals -- dense sensitivities (the one-step masks below hold for Euler /
     // linearised steps only); bit 1: finite bounds -- primal-dual interior point (T1's algorithm, mmpc_solve_t1.cuh)
-    static constexpr int RK = RK_ & 1, BD = (RK_ >> 1) & 1;
+    static constexpr int MODE = RK_, RK = RK_ & 1, BD = (RK_ >> 1) & 1;
     static constexpr bool SPARSE = !RK && NX * NX <= 64 && NX * NU <= 64;
     static constexpr unsigned long long fx_mask() {
         unsigned long long m = SPARSE ? M::A_MASK : ~0ULL;
@@ -107,14 +107,21 @@ __device__ __forceinline__ void t3_st_evict_last(double* p, double v) {
 #define T3_FXSLOT(a) (C::SPARSE ? __popcll(C::FXM & ((1ULL << (a)) - 1ULL)) : (a))
 #define T3_FUSLOT(a) (C::SPARSE ? __popcll(C::FUM & ((1ULL << (a)) - 1ULL)) : (a))
 
-template <class M, int I_, int RK_ = 0>
-struct T3Ctx {
+// bounded problems only: multipliers of the lower / upper bounds and their steps, in V layout like the iterate
+template <bool BD>
+struct T3CtxBounds {};
+template <>
+struct T3CtxBounds<true> {
+    double *ZL, *ZU, *DZL, *DZU;
+};
+
+template <class M, int I_, int MODE_ = 0>
+struct T3Ctx : T3CtxBounds<((MODE_ >> 1) & 1) != 0> {
     static constexpr int NX = M::NX, NU = M::NU, S = NX + NU, I = I_;
     const mmpc_problem& P;
     int N;
     double *V, *LAM, *DV, *LAMN;  // this thread's instance inside the tile arrays: element e lives at [e * I]
     double* LINp;                 // linearisation data of the instance (AoS)
-    double *ZL, *ZU, *DZL, *DZU;  // bounded: multipliers of the lower / upper bounds and their steps, in V layout like the iterate
     const double* traj;
     double Q[NX], R[NU], Rm[NU], uinit[NU];
     __device__ T3Ctx(const mmpc_problem& P_) : P(P_) {}
@@ -125,7 +132,7 @@ struct T3Ctx {
             double x0[NX];
             MMPC_UNROLL for (int i = 0; i < NX; ++i) x0[i] = V[(size_t)i * I];
             step_linear<M, WANT>(P.h, x, u, LINp, LINp + NX * NX, LINp + NX * NX + NX * NU, x0, uinit, F, Fx, Fu, Hs);
-        } else if (RK_) {
+        } else if (MODE_ & 1) {
             step_rk4<M, (WANT >= 1 ? 1 : 0)>(P.h, P.substeps, x, u, F, Fx, Fu);
             if (WANT >= 2) MMPC_UNROLL for (int i = 0; i < S * (S + 1) / 2; ++i) Hs[i] = 0.0;  // Gauss-Newton Hessian under RK4
         } else {
@@ -138,7 +145,7 @@ struct T3Ctx {
 // starts with a dependent chain of L2 round trips)
 __device__ __forceinline__ void t3_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 template <class M, class C>
-__device__ __forceinline__ void t3_prefetch_node(const T3Ctx<M, C::I, C::RK>& c, int k) {
+__device__ __forceinline__ void t3_prefetch_node(const T3Ctx<M, C::I, C::MODE>& c, int k) {
     constexpr int NX = M::NX, S = C::S, I = C::I;
     const double* z = c.V + (size_t)k * S * I;
     MMPC_UNROLL for (int a = 0; a < S + NX; ++a) t3_prefetch(z + a * I);  // x_k, u_k, x_{k+1}; u_{k-1} and u_{k+1} belong to the neighbours
@@ -149,7 +156,7 @@ __device__ __forceinline__ void t3_prefetch_node(const T3Ctx<M, C::I, C::RK>& c,
 // ---- parallel phase of the backward sweep: thread (i, j) evaluates node k = k0 + j of instance i -------------
 // red slots: 0 dual_inf(max) 1 prim_inf(max) 2 theta 3 fval 4 lam_l1
 template <class M, class C>
-__device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I, C::RK>& c, int k, int i, int j, double delta, double mu, double* rec, double* red,
+__device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I, C::MODE>& c, int k, int i, int j, double delta, double mu, double* rec, double* red,
                                              double* fg_tile) {
     constexpr int NX = M::NX, NU = M::NU, S = C::S, NH = C::NH, I = C::I;
     const int N = c.N;
@@ -400,10 +407,10 @@ struct T3Norms {
 // lane per instance) the worker warps evaluate chunk ch-1 into the other record buffer.
 // returns (valid on the serial lanes) whether every G_uu was positive definite
 template <class M, class C>
-__device__ __noinline__ bool t3_backward(const T3Ctx<M, C::I, C::RK>& cin, double* smem, int tid, double delta_self, T3Norms& nrm_out,
+__device__ __noinline__ bool t3_backward(const T3Ctx<M, C::I, C::MODE>& cin, double* smem, int tid, double delta_self, T3Norms& nrm_out,
                                          double* fg_tile, double* kg_tile, double* pg_tile) {
     constexpr int NX = M::NX, NU = M::NU, I = C::I;
-    const T3Ctx<M, C::I, C::RK> c = cin;  // callee-local copy: the context and all accumulators stay in registers (the caller's copy has
+    const T3Ctx<M, C::I, C::MODE> c = cin;  // callee-local copy: the context and all accumulators stay in registers (the caller's copy has
                              // its address taken and therefore lives in local memory)
     const int N = c.N;
     const bool worker = C::is_worker(tid);
@@ -487,9 +494,9 @@ struct T3NormsBD {
     double dual_inf, prim_inf, theta, fval, lam_l1, z_l1, cmax, cmin, barrier;
 };
 template <class M, class C>
-__device__ __noinline__ void t3_residuals(const T3Ctx<M, C::I, C::RK>& cin, double* smem, int tid, T3NormsBD& out) {
+__device__ __noinline__ void t3_residuals(const T3Ctx<M, C::I, C::MODE>& cin, double* smem, int tid, T3NormsBD& out) {
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
-    const T3Ctx<M, C::I, C::RK> c = cin;
+    const T3Ctx<M, C::I, C::MODE> c = cin;
     const int N = c.N;
     const bool worker = C::is_worker(tid);
     const int w = C::widx(tid), wi = w % I, wj = w / I;
@@ -586,7 +593,7 @@ struct T3TrialBD {
     bool full;
 };
 template <class M, class C>
-__device__ __forceinline__ void t3_trial_node(const T3Ctx<M, C::I, C::RK>& c, int k, double alpha, double& f1, double& th1, T3TrialBD& bd) {
+__device__ __forceinline__ void t3_trial_node(const T3Ctx<M, C::I, C::MODE>& c, int k, double alpha, double& f1, double& th1, T3TrialBD& bd) {
     constexpr int NX = M::NX, NU = M::NU, S = NX + NU, I = C::I;
     const double* z = c.V + (size_t)k * S * I;
     const double* d = c.DV + (size_t)k * S * I;
@@ -646,10 +653,10 @@ struct T3Fwd {
 // forward sweep for the tile, software pipelined: while warp 0 rolls the step through chunk ch, the worker warps stage
 // chunk ch+1's records (cp.async) and evaluate the merit terms of the full step on chunk ch-1.
 template <class M, class C>
-__device__ __noinline__ void t3_forward(const T3Ctx<M, C::I, C::RK>& cin, double* smem, int tid, T3Fwd& o_out, const double* fg_tile, const double* kg_tile,
+__device__ __noinline__ void t3_forward(const T3Ctx<M, C::I, C::MODE>& cin, double* smem, int tid, T3Fwd& o_out, const double* fg_tile, const double* kg_tile,
                                         const double* pg_tile) {
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
-    const T3Ctx<M, C::I, C::RK> c = cin;  // register-resident copies (see t3_backward)
+    const T3Ctx<M, C::I, C::MODE> c = cin;  // register-resident copies (see t3_backward)
     T3Fwd o;
     const int N = c.N;
     const bool worker = C::is_worker(tid);
@@ -784,9 +791,9 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I, C::RK>& cin, double
 
 // merit of z + alpha_i dz for every instance of the tile (alpha per instance in shared memory)
 template <class M, class C>
-__device__ __noinline__ void t3_trial(const T3Ctx<M, C::I, C::RK>& cin, double* smem, int tid, double& f1, double& th1, double& bar1) {
+__device__ __noinline__ void t3_trial(const T3Ctx<M, C::I, C::MODE>& cin, double* smem, int tid, double& f1, double& th1, double& bar1) {
     constexpr int I = C::I;
-    const T3Ctx<M, C::I, C::RK> c = cin;
+    const T3Ctx<M, C::I, C::MODE> c = cin;
     const bool worker = C::is_worker(tid);
     const int w = C::widx(tid), wi = w % I, wj = w / I;
     double* red = smem + C::SM_RED;
@@ -829,14 +836,16 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
     const bool valid = b >= io.b0 && b < io.b1;
     const int bi = valid ? b : io.b1 - 1;       // surplus slots read the last instance's inputs and never write outputs
 
-    T3Ctx<M, I, C::RK> c(P);
+    T3Ctx<M, I, C::MODE> c(P);
     c.N = N;
     // the iterate lives tile-wise, [element][instance]: every access of a warp is a run of full sectors whatever I is
     c.V = W.V2 + (size_t)tile * I * NV + i; c.LAM = W.LAM2 + (size_t)tile * I * Mc + i;
     c.DV = W.DV2 + (size_t)tile * I * NV + i; c.LAMN = W.LAMN2 + (size_t)tile * I * Mc + i;
     c.LINp = W.LIN2 + (size_t)b * C::LIN;
-    c.ZL = W.ZL2 + (size_t)tile * I * NV + i; c.ZU = W.ZU2 + (size_t)tile * I * NV + i;
-    c.DZL = W.DZL2 + (size_t)tile * I * NV + i; c.DZU = W.DZU2 + (size_t)tile * I * NV + i;
+    if constexpr (C::BD != 0) {
+        c.ZL = W.ZL2 + (size_t)tile * I * NV + i; c.ZU = W.ZU2 + (size_t)tile * I * NV + i;
+        c.DZL = W.DZL2 + (size_t)tile * I * NV + i; c.DZU = W.DZU2 + (size_t)tile * I * NV + i;
+    }
     c.traj = io.traj + (size_t)bi * N * NX;
     double* fg_tile = W.FG2 + (size_t)tile * I * N * C::FG;
     double* kg_tile = W.KG2 + (size_t)tile * I * N * C::KG;
