@@ -824,7 +824,7 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
     extern __shared__ __align__(16) double smem[];
 #ifdef MMPC_T3_PROFILE
     const long long t_entry = clock64();
-    long long t_bwd[8] = {0}, t_fwd[8] = {0}, t_post[8] = {0};
+    long long t_bwd[8] = {0}, t_fwd[8] = {0}, t_post[8] = {0}, t_res[8] = {0};
 #endif
     const int tid = threadIdx.x, tile = io.b0 / C::I + blockIdx.x;  // b0 is a multiple of 32*I-compatible tile starts
     const bool worker = C::is_worker(tid);
@@ -914,7 +914,13 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
         if constexpr (C::BD) {
             // residuals first: the barrier parameter is chosen from them (T1's bounded iteration, mmpc_solve_t1.cuh)
             T3NormsBD nb;
+#ifdef MMPC_T3_PROFILE
+            const long long tr0 = clock64();
+#endif
             t3_residuals<M, C>(c, smem, tid, nb);
+#ifdef MMPC_T3_PROFILE
+            if (it < 8) t_res[it] = clock64() - tr0;
+#endif
             nrm.dual_inf = nb.dual_inf; nrm.prim_inf = nb.prim_inf; nrm.theta = nb.theta; nrm.fval = nb.fval; nrm.lam_l1 = nb.lam_l1;
             barrier0 = nb.barrier;
             if (active) {
@@ -937,7 +943,13 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
             if (tid < I) sh_mu[tid] = mu;
             if (!__syncthreads_or(active)) break;
             T3Norms unused;
+#ifdef MMPC_T3_PROFILE
+            const long long tp0 = clock64();
+#endif
             ok = t3_backward<M, C>(c, smem, tid, delta, unused, fg_tile, kg_tile, pg_tile);
+#ifdef MMPC_T3_PROFILE
+            if (it < 8) t_bwd[it] = clock64() - tp0;
+#endif
         } else {
 #ifdef MMPC_T3_PROFILE
         const long long tp0 = clock64();
@@ -1070,7 +1082,7 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
     if (blockIdx.x == 0 && tid == 0) {
         const long long t_end = clock64();
         printf("[t3 kernel] prologue %lld  loop %lld  epilogue %lld cycles, %d iterations\n", t_kernel0 - t_entry, t_loop_end - t_kernel0, t_end - t_loop_end, it);
-        for (int q = 0; q <= it && q < 8; ++q) printf("[t3 it %d] backward %lld  forward %lld  line search + step %lld\n", q, t_bwd[q], t_fwd[q], t_post[q]);
+        for (int q = 0; q <= it && q < 8; ++q) printf("[t3 it %d] residuals %lld  backward %lld  forward %lld  line search + step %lld\n", q, t_res[q], t_bwd[q], t_fwd[q], t_post[q]);
     }
 #endif
 }

@@ -10,6 +10,8 @@ m = api.Model("double_pendulum", N=N)
 for B in [int(a) for a in sys.argv[2:]]:
     x0, up, traj = workload.synthetic_batch(4, 2, N, 0.002, B)
     s = api.Solver(m, B, warm_start=0, kernel_variant=v); s.set_weights(Q, R, Rm)
+    if os.environ.get("MMPC_UBOUND"):
+        ub = float(os.environ["MMPC_UBOUND"]); s.set_bounds(u_min=[-ub, -ub], u_max=[ub, ub])
     for rep in range(2):
         if os.environ.get("MMPC_DEV"):  # device-resident inputs (single launch, no sub-batches)
             import torch
