@@ -84,7 +84,9 @@ typedef struct mmpc_options {
     int warm_start;        /* 1: start from the previous solution of the same instance slot
                                  (ModelControl.cpp:161: args["x0"] = result), 0: always cold (zeros) */
     int warm_start_duals;  /* 0: reference behaviour (primal only); 1: also reuse lam_g */
-    int kernel_variant;    /* 0 = auto; see DESIGN.md "kernels" */
+    int kernel_variant;    /* 0 = auto: T3 for nx+2nu <= 8, else T2; T1 for what those do not implement.
+                              1 / 2 / 3 request T1 / T2 / T3; 3 + 256*k forces T3's tile configuration k (1 = 8x4x4,
+                              2 = 32x7x5) -- experiments and tests only.  Changing it forgets the warm start. */
     int reserved[8];
 } mmpc_options;
 
