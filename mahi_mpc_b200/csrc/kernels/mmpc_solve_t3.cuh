@@ -354,22 +354,40 @@ __device__ __forceinline__ bool t3_riccati_stage(T3Riccati<M>& V, const double* 
         MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FUNZ(q, a)) t = fma(Fu[q * NU + a], y[q], t);
         gu[a] = t;
     }
-    const bool ok = chol<NU>(Guu);
+    bool ok;
     double Kx[NU * NX], Kv[NU * NU], k0[NU];
-    MMPC_UNROLL for (int a = 0; a < NX; ++a) {
-        double col[NU];
-        MMPC_UNROLL for (int b = 0; b < NU; ++b) col[b] = -Gxu[a * NU + b];
-        chol_solve<NU>(Guu, col);
-        MMPC_UNROLL for (int b = 0; b < NU; ++b) Kx[b * NX + a] = col[b];
+    if constexpr (NU == 2) {
+        // two controls: explicit inverse of the 2 x 2 block (one reciprocal on the stage's dependent chain instead of the two
+        // dependent rsqrt of the Cholesky factor and its substitutions); positive definite <=> G00 > 0 and det > 0
+        const double det = fma(Guu[0], Guu[3], -Guu[1] * Guu[1]);
+        ok = (Guu[0] > 0.0) && (det > 0.0) && isfinite(det);
+        const double r = 1.0 / (ok ? det : 1.0);
+        const double i00 = Guu[3] * r, i01 = -Guu[1] * r, i11 = Guu[0] * r;
+        MMPC_UNROLL for (int a = 0; a < NX; ++a) {
+            Kx[0 * NX + a] = -fma(i00, Gxu[a * NU + 0], i01 * Gxu[a * NU + 1]);
+            Kx[1 * NX + a] = -fma(i01, Gxu[a * NU + 0], i11 * Gxu[a * NU + 1]);
+        }
+        Kv[0 * NU + 0] = i00 * (2.0 * R[0]); Kv[1 * NU + 0] = i01 * (2.0 * R[0]);
+        Kv[0 * NU + 1] = i01 * (2.0 * R[1]); Kv[1 * NU + 1] = i11 * (2.0 * R[1]);
+        k0[0] = -fma(i00, gu[0], i01 * gu[1]);
+        k0[1] = -fma(i01, gu[0], i11 * gu[1]);
+    } else {
+        ok = chol<NU>(Guu);
+        MMPC_UNROLL for (int a = 0; a < NX; ++a) {
+            double col[NU];
+            MMPC_UNROLL for (int b = 0; b < NU; ++b) col[b] = -Gxu[a * NU + b];
+            chol_solve<NU>(Guu, col);
+            MMPC_UNROLL for (int b = 0; b < NU; ++b) Kx[b * NX + a] = col[b];
+        }
+        MMPC_UNROLL for (int l = 0; l < NU; ++l) {
+            double col[NU];
+            MMPC_UNROLL for (int b = 0; b < NU; ++b) col[b] = (b == l) ? 2.0 * R[l] : 0.0;
+            chol_solve<NU>(Guu, col);
+            MMPC_UNROLL for (int b = 0; b < NU; ++b) Kv[b * NU + l] = col[b];
+        }
+        MMPC_UNROLL for (int b = 0; b < NU; ++b) k0[b] = -gu[b];
+        chol_solve<NU>(Guu, k0);
     }
-    MMPC_UNROLL for (int l = 0; l < NU; ++l) {
-        double col[NU];
-        MMPC_UNROLL for (int b = 0; b < NU; ++b) col[b] = (b == l) ? 2.0 * R[l] : 0.0;
-        chol_solve<NU>(Guu, col);
-        MMPC_UNROLL for (int b = 0; b < NU; ++b) Kv[b * NU + l] = col[b];
-    }
-    MMPC_UNROLL for (int b = 0; b < NU; ++b) k0[b] = -gu[b];
-    chol_solve<NU>(Guu, k0);
     MMPC_UNROLL for (int a = 0; a < NU * NX; ++a) T3_ST(&kg[(C::KG_KX + a) * I], Kx[a]);
     MMPC_UNROLL for (int a = 0; a < NU * NU; ++a) T3_ST(&kg[(C::KG_KV + a) * I], Kv[a]);
     MMPC_UNROLL for (int a = 0; a < NU; ++a) T3_ST(&kg[(C::KG_K0 + a) * I], k0[a]);
