@@ -35,6 +35,10 @@ struct T3 {
     static constexpr int THREADS = 32 + WORKERS + (SK ? 32 : 0);
     __device__ static __forceinline__ bool is_worker(int tid) { return tid >= 32 && !(SK && tid >= 128 && tid < 160); }
     __device__ static __forceinline__ int widx(int tid) { return tid - 32 - ((SK && tid >= 160) ? 32 : 0); }
+    // Node slot of worker group g = widx / I.  With one warp per slot (I = 32) warp 4 shares its SM sub-partition -- and its
+    // fp64 pipe -- with the serial warp (warp 0): it gets the LAST slot, which the balanced chunks leave empty most of the
+    // time (N = 50, CB = 7: 6 of 8 chunks have 6 nodes) and which takes no part in the forward sweep's merit evaluation.
+    __device__ static __forceinline__ int slot_of(int g) { return (I == 32 && CB > 4) ? (g == 3 ? CB - 1 : (g == CB - 1 ? 3 : g)) : g; }
     // Fx and Fu are stored compacted to their structural non-zeros (generator masks; dense if a mask does not fit 64 bits);
     // the value-function block Pxx is stored as its upper triangle
     // RK_ is a mode mask.  bit 0: RK4 shooting intervals -- dense sensitivities (the one-step masks below hold for Euler /
@@ -432,7 +436,7 @@ __device__ __noinline__ bool t3_backward(const T3Ctx<M, C::I, C::MODE>& cin, dou
                              // its address taken and therefore lives in local memory)
     const int N = c.N;
     const bool worker = C::is_worker(tid);
-    const int w = C::widx(tid), wi = w % I, wj = w / I;
+    const int w = C::widx(tid), wi = w % I, wj = C::slot_of(w / I);
     double* dl = smem + C::SM_INST;  // per-instance delta, published by the serial lanes
     double n_dual = 0.0, n_prim = 0.0, n_theta = 0.0, n_fval = 0.0, n_lam = 0.0;
     bool ok = true;
@@ -517,7 +521,7 @@ __device__ __noinline__ void t3_residuals(const T3Ctx<M, C::I, C::MODE>& cin, do
     const T3Ctx<M, C::I, C::MODE> c = cin;
     const int N = c.N;
     const bool worker = C::is_worker(tid);
-    const int w = C::widx(tid), wi = w % I, wj = w / I;
+    const int w = C::widx(tid), wi = w % I, wj = C::slot_of(w / I);
     double* red = smem + C::SM_RED;
     if (worker) {
         SweepNorms n;
@@ -678,7 +682,7 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I, C::MODE>& cin, doub
     T3Fwd o;
     const int N = c.N;
     const bool worker = C::is_worker(tid);
-    const int w = C::widx(tid), wi = w % I, wj = w / I;
+    const int w = C::widx(tid), wi = w % I, wj = C::slot_of(w / I);
     double* red = smem + C::SM_RED;
     double dx[NX], dv[NU];
     MMPC_UNROLL for (int a = 0; a < NX; ++a) dx[a] = 0.0;
@@ -813,7 +817,7 @@ __device__ __noinline__ void t3_trial(const T3Ctx<M, C::I, C::MODE>& cin, double
     constexpr int I = C::I;
     const T3Ctx<M, C::I, C::MODE> c = cin;
     const bool worker = C::is_worker(tid);
-    const int w = C::widx(tid), wi = w % I, wj = w / I;
+    const int w = C::widx(tid), wi = w % I, wj = C::slot_of(w / I);
     double* red = smem + C::SM_RED;
     if (worker) {
         const double alpha = smem[C::SM_INST + I + wi];
@@ -848,7 +852,7 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
     const bool worker = C::is_worker(tid);
     // a thread's instance: serial lane tid -> instance tid; worker w -> instance w % I (node slot w / I)
     const int i = worker ? C::widx(tid) % I : (tid < I ? tid : 0);
-    const int j = worker ? C::widx(tid) / I : 0;
+    const int j = worker ? C::slot_of(C::widx(tid) / I) : 0;
     const int N = P.N, NV = NX * (N + 1) + NU * N, Mc = N * NX;
     const int b = tile * I + i;                 // workspace slot (arrays are sized for the batch padded to 32)
     const bool valid = b >= io.b0 && b < io.b1;
