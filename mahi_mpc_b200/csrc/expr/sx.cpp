@@ -497,6 +497,25 @@ std::string emit_body(const std::vector<EmitInput>& ins, const std::vector<EmitO
         if (n.op == Op::Const || n.op == Op::Sym) continue;
         if (done.count(id)) continue;
         const std::string v = "v" + std::to_string(id);
+        // CUDA only: sin/cos of a sum or difference whose terms' sin and cos are already available come from the angle
+        // addition formulas (4 multiply-adds instead of a ~60-instruction fp64 sincos; error a few ulp).  The C emitters
+        // keep the plain calls.
+        if (cuda && (n.op == Op::Sin || n.op == Op::Cos)) {
+            const Node& arg = g.node(n.a);
+            if (arg.op == Op::Add || arg.op == Op::Sub) {
+                auto have = [&](int t) { return sin_of.count(t) && cos_of.count(t) && nm.count(sin_of[t]) && nm.count(cos_of[t]); };
+                if (have(arg.a) && have(arg.b)) {
+                    const std::string sp = nm[sin_of[arg.a]], cp = nm[cos_of[arg.a]], sq = nm[sin_of[arg.b]], cq = nm[cos_of[arg.b]];
+                    const bool add = arg.op == Op::Add;
+                    os << ind << "const double " << v << " = ";
+                    if (n.op == Op::Sin) os << "fma(" << sp << ", " << cq << ", " << (add ? "" : "-") << cp << " * " << sq << ")";
+                    else os << "fma(" << cp << ", " << cq << ", " << (add ? "-" : "") << sp << " * " << sq << ")";
+                    os << ";\n";
+                    nm[id] = v;
+                    continue;
+                }
+            }
+        }
         if ((n.op == Op::Sin || n.op == Op::Cos) && sin_of.count(n.a) && cos_of.count(n.a)) {
             const int sid = sin_of[n.a], cid = cos_of[n.a];
             os << ind << "double v" << sid << ", v" << cid << "; " << (cuda ? "MMPC_SINCOS(" : "sincos(") << ref(n.a) << ", &v" << sid << ", &v" << cid << ");\n";
