@@ -484,6 +484,22 @@ std::string emit_body(const std::vector<EmitInput>& ins, const std::vector<EmitO
         if (n.op == Op::Sin) sin_of[n.a] = id;
         if (n.op == Op::Cos) cos_of[n.a] = id;
     }
+    // CUDA only: sin/cos of a sum or difference come from the angle addition formulas when sin and cos of both terms are
+    // computed anyway (4 multiply-adds instead of a ~60-instruction fp64 sincos; error a few ulp).  A term that has only
+    // its sin or only its cos in this function gets the other one from the same sincos call, so that every function
+    // emitted from one graph evaluates the shared sub-expressions identically.  The C emitters keep the plain calls.
+    std::unordered_map<int, bool> want_both;
+    if (cuda) {
+        for (int id : order) {
+            const Node& n = g.node(id);
+            if (n.op != Op::Sin && n.op != Op::Cos) continue;
+            const Node& arg = g.node(n.a);
+            if (arg.op != Op::Add && arg.op != Op::Sub) continue;
+            auto trig = [&](int t) { return sin_of.count(t) || cos_of.count(t); };
+            if (trig(arg.a) && trig(arg.b)) want_both[arg.a] = want_both[arg.b] = true;
+        }
+    }
+    std::unordered_map<int, std::string> sin_nm, cos_nm;  // argument id -> name of its emitted sin / cos
     auto ref = [&](int id) -> std::string {
         const Node& n = g.node(id);
         if (n.op == Op::Const) return n.val < 0 ? "(" + fmt_double(n.val) + ")" : fmt_double(n.val);
@@ -497,31 +513,28 @@ std::string emit_body(const std::vector<EmitInput>& ins, const std::vector<EmitO
         if (n.op == Op::Const || n.op == Op::Sym) continue;
         if (done.count(id)) continue;
         const std::string v = "v" + std::to_string(id);
-        // CUDA only: sin/cos of a sum or difference whose terms' sin and cos are already available come from the angle
-        // addition formulas (4 multiply-adds instead of a ~60-instruction fp64 sincos; error a few ulp).  The C emitters
-        // keep the plain calls.
         if (cuda && (n.op == Op::Sin || n.op == Op::Cos)) {
             const Node& arg = g.node(n.a);
-            if (arg.op == Op::Add || arg.op == Op::Sub) {
-                auto have = [&](int t) { return sin_of.count(t) && cos_of.count(t) && nm.count(sin_of[t]) && nm.count(cos_of[t]); };
-                if (have(arg.a) && have(arg.b)) {
-                    const std::string sp = nm[sin_of[arg.a]], cp = nm[cos_of[arg.a]], sq = nm[sin_of[arg.b]], cq = nm[cos_of[arg.b]];
-                    const bool add = arg.op == Op::Add;
-                    os << ind << "const double " << v << " = ";
-                    if (n.op == Op::Sin) os << "fma(" << sp << ", " << cq << ", " << (add ? "" : "-") << cp << " * " << sq << ")";
-                    else os << "fma(" << cp << ", " << cq << ", " << (add ? "-" : "") << sp << " * " << sq << ")";
-                    os << ";\n";
-                    nm[id] = v;
-                    continue;
-                }
+            if ((arg.op == Op::Add || arg.op == Op::Sub) && sin_nm.count(arg.a) && cos_nm.count(arg.a) && sin_nm.count(arg.b) && cos_nm.count(arg.b)) {
+                const std::string sp = sin_nm[arg.a], cp = cos_nm[arg.a], sq = sin_nm[arg.b], cq = cos_nm[arg.b];
+                const bool add = arg.op == Op::Add;
+                os << ind << "const double " << v << " = ";
+                if (n.op == Op::Sin) os << "fma(" << sp << ", " << cq << ", " << (add ? "" : "-") << cp << " * " << sq << ")";
+                else os << "fma(" << cp << ", " << cq << ", " << (add ? "-" : "") << sp << " * " << sq << ")";
+                os << ";\n";
+                nm[id] = v;
+                (n.op == Op::Sin ? sin_nm : cos_nm)[n.a] = v;
+                continue;
             }
         }
-        if ((n.op == Op::Sin || n.op == Op::Cos) && sin_of.count(n.a) && cos_of.count(n.a)) {
-            const int sid = sin_of[n.a], cid = cos_of[n.a];
-            os << ind << "double v" << sid << ", v" << cid << "; " << (cuda ? "MMPC_SINCOS(" : "sincos(") << ref(n.a) << ", &v" << sid << ", &v" << cid << ");\n";
-            nm[sid] = "v" + std::to_string(sid);
-            nm[cid] = "v" + std::to_string(cid);
-            done[sid] = done[cid] = true;
+        if ((n.op == Op::Sin || n.op == Op::Cos) && ((sin_of.count(n.a) && cos_of.count(n.a)) || want_both.count(n.a))) {
+            const std::string sname = sin_of.count(n.a) ? "v" + std::to_string(sin_of[n.a]) : "s" + std::to_string(n.a);
+            const std::string cname = cos_of.count(n.a) ? "v" + std::to_string(cos_of[n.a]) : "c" + std::to_string(n.a);
+            os << ind << "double " << sname << ", " << cname << "; " << (cuda ? "MMPC_SINCOS(" : "sincos(") << ref(n.a) << ", &" << sname << ", &" << cname << ");\n";
+            if (sin_of.count(n.a)) { nm[sin_of[n.a]] = sname; done[sin_of[n.a]] = true; }
+            if (cos_of.count(n.a)) { nm[cos_of[n.a]] = cname; done[cos_of[n.a]] = true; }
+            sin_nm[n.a] = sname;
+            cos_nm[n.a] = cname;
             continue;
         }
         os << ind << "const double " << v << " = ";
