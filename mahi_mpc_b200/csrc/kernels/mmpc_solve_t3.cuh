@@ -16,7 +16,7 @@
 //   * the two run concurrently on double-buffered records: one __syncthreads per chunk, no other synchronisation.
 // One launch per batched solve; no grid-wide synchronisation.  Replaces IPOPT+MUMPS at ModelControl.cpp:159.
 #pragma once
-#if defined(MMPC_T3_PROFILE) || defined(MMPC_T3_PROFILE_SWEEPS)
+#if defined(MMPC_T3_PROFILE) || defined(MMPC_T3_PROFILE_SWEEPS) || defined(MMPC_T3_PROFILE_CTAS)
 #include <cstdio>
 #endif
 
@@ -615,12 +615,18 @@ struct T3TrialBD {
     bool full;
 };
 template <class M, class C>
-__device__ __forceinline__ void t3_trial_node(const T3Ctx<M, C::I, C::MODE>& c, int k, double alpha, double& f1, double& th1, T3TrialBD& bd) {
+__device__ __forceinline__ void t3_trial_node(const T3Ctx<M, C::I, C::MODE>& c, int k, double alpha, double& f1, double& th1, T3TrialBD& bd,
+                                              bool keep_lam = false) {
     constexpr int NX = M::NX, NU = M::NU, S = NX + NU, I = C::I;
     const double* z = c.V + (size_t)k * S * I;
     const double* d = c.DV + (size_t)k * S * I;
     double x[NX], u[NU], v[NU], xn[NX], F[NX], r[NX];
     MMPC_UNROLL for (int a = 0; a < NX; ++a) r[a] = c.traj[(size_t)k * NX + a];  // with the other loads: one L2 round trip, not two
+    if (keep_lam) {  // forward sweep, instance that no longer iterates: LAMN must hold its multipliers when LAM and LAMN swap
+        double lk[NX];
+        MMPC_UNROLL for (int a = 0; a < NX; ++a) lk[a] = c.LAM[((size_t)k * NX + a) * I];
+        MMPC_UNROLL for (int a = 0; a < NX; ++a) c.LAMN[((size_t)k * NX + a) * I] = lk[a];
+    }
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         x[a] = fma(alpha, d[a * I], z[a * I]);
         xn[a] = fma(alpha, d[(S + a) * I], z[(S + a) * I]);
@@ -705,13 +711,16 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I, C::MODE>& cin, doub
         }
     };
     double f1 = 0.0, th1 = 0.0;  // worker-local merit sums
+    // does this thread's instance still iterate?  lam+ goes to LAMN, which swaps with LAM when the step is accepted: the serial
+    // lane writes it for the instances that iterate, the merit worker of a node copies the old multipliers for the others
+    const bool act = smem[C::SM_INST + 2 * I + (worker ? wi : (tid < I ? tid : 0))] != 0.0;
     T3TrialBD bd;
     bd.bar1 = 0.0; bd.amax = bd.az = 1.0; bd.full = true;
     bd.mu = C::BD ? smem[C::SM_INST + 3 * I + (worker ? wi : 0)] : 0.0;
     bd.tau = fmax(0.99, 1.0 - bd.mu);  // IPOPT tau_min = 0.99 [upstream]
     auto trial_chunk = [&](int ch) {  // workers with node slot < CF take part
         const int k0 = ch * C::CF, kn = min(C::CF, N - k0);
-        if (wj < kn) t3_trial_node<M, C>(c, k0 + wj, 1.0, f1, th1, bd);
+        if (wj < kn) t3_trial_node<M, C>(c, k0 + wj, 1.0, f1, th1, bd, !act);
     };
 #ifdef MMPC_T3_PROFILE_SWEEPS
     long long t_work = 0, t_all0 = clock64();
@@ -767,7 +776,7 @@ __device__ __noinline__ void t3_forward(const T3Ctx<M, C::I, C::MODE>& cin, doub
                     double t = T3_F(C::RF_P + C::PG_X + a);
                     MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(T3_F(C::RF_P + C::PG_XX + trisym(a, q, NX)), dxn[q], t);
                     MMPC_UNROLL for (int q = 0; q < NU; ++q) t = fma(T3_F(C::RF_P + C::PG_XV + a * NU + q), du[q], t);
-                    c.LAMN[((size_t)k * NX + a) * I] = t;
+                    if (act) c.LAMN[((size_t)k * NX + a) * I] = t;
                     o.lam_inf = fmax(o.lam_inf, fabs(t));
                     o.finite = o.finite && isfinite(t) && isfinite(dxn[a]);
                 }
@@ -844,9 +853,15 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
     using C = T3<M, I_, CB_, CF_, SK_, RK_>;
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
     extern __shared__ __align__(16) double smem[];
+#ifdef MMPC_T3_PROFILE_CTAS
+    unsigned long long gt0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+#endif
 #ifdef MMPC_T3_PROFILE
     const long long t_entry = clock64();
-    long long t_bwd[8] = {0}, t_fwd[8] = {0}, t_post[8] = {0}, t_res[8] = {0};
+    long long t_bwd[8] = {0}, t_fwd[8] = {0}, t_post[8] = {0}, t_res[8] = {0}, t_glue[4] = {0}, t_iter[8] = {0}, t_it0 = 0, ts[10] = {0};
 #endif
     const int tid = threadIdx.x, tile = io.b0 / C::I + blockIdx.x;  // b0 is a multiple of 32*I-compatible tile starts
     const bool worker = C::is_worker(tid);
@@ -915,7 +930,7 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
 
     // plain local copies for the element-wise loops below (the struct `c` is passed by reference to the sweeps, so it lives
     // in local memory; these do not)
-    double* const Vp = c.V; double* const LAMp = c.LAM; const double* const DVp = c.DV; const double* const LAMNp = c.LAMN;
+    double* const Vp = c.V; const double* const DVp = c.DV;
     // per-instance solver state lives in the serial lane (tid < I) of the instance
     double nu_merit = 1.0, delta_last = 0.0, err = INFINITY, fval = 0.0;
     int it = 0, it_done = 0, status = MMPC_SOLVE_MAX_ITER, ls_total = 0, reg_total = 0;
@@ -930,6 +945,9 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
     double* sh_mu = smem + C::SM_INST + 3 * I;  // per-instance barrier parameter
     double* sh_az = smem + C::SM_INST + 4 * I;  // per-instance step length of the bound multipliers
     for (it = 0;; ++it) {
+#ifdef MMPC_T3_PROFILE
+        { const long long tn = clock64(); if (it > 0 && it <= 8) t_iter[it - 1] = tn - t_it0; t_it0 = tn; if (it == 1) ts[0] = tn; if (it == 2) ts[9] = tn; }
+#endif
         T3Norms nrm;
         double delta = 0.0;
         bool ok = true;
@@ -975,9 +993,11 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
         } else {
 #ifdef MMPC_T3_PROFILE
         const long long tp0 = clock64();
+        if (it == 1) ts[1] = tp0;
 #endif
         ok = t3_backward<M, C>(c, smem, tid, delta, nrm, fg_tile, kg_tile, pg_tile);
 #ifdef MMPC_T3_PROFILE
+        if (it == 1) ts[2] = clock64();
         if (it < 8) t_bwd[it] = clock64() - tp0;
 #endif
         if (active) {
@@ -990,7 +1010,14 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
             else if (it >= io.max_iter) { status = MMPC_SOLVE_MAX_ITER; active = false; }
         }
         }
+#ifdef MMPC_T3_PROFILE
+        const long long tg0 = clock64();
+        if (it == 1) ts[3] = tg0;
+#endif
         if (!__syncthreads_or(active)) break;
+#ifdef MMPC_T3_PROFILE
+        const long long tg1 = clock64();
+#endif
         int tries = 0;
         while (__syncthreads_or(active && !ok)) {  // inertia correction for the instances that need it
             if (active && !ok) {
@@ -1006,14 +1033,23 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
             }
         }
         if (delta > 0.0) delta_last = delta;
+        if (tid < I) sh_flag[tid] = active ? 1.0 : 0.0;  // which instances still iterate: read by the forward sweep
+#ifdef MMPC_T3_PROFILE
+        const long long tg2 = clock64();
+#endif
         if (!__syncthreads_or(active)) break;
+#ifdef MMPC_T3_PROFILE
+        if (it == 1 && blockIdx.x == 0 && tid == 0) { t_glue[0] = tg1 - tg0; t_glue[1] = tg2 - tg1; t_glue[2] = clock64() - tg2; }
+#endif
         T3Fwd fo;
 #ifdef MMPC_T3_PROFILE
         const long long tp1 = clock64();
+        if (it == 1) { ts[4] = tg2; ts[5] = tp1; }
 #endif
         t3_forward<M, C>(c, smem, tid, fo, fg_tile, kg_tile, pg_tile);
 #ifdef MMPC_T3_PROFILE
         const long long tp2 = clock64();
+        if (it == 1) ts[6] = tp2;
         if (it < 8) t_fwd[it] = tp2 - tp1;
 #endif
         if (active && !(fo.finite && isfinite(fo.f1))) { status = MMPC_SOLVE_NUMERICAL; active = false; }
@@ -1039,25 +1075,27 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
             t3_trial<M, C>(c, smem, tid, f2, t2, b2);
             if (need) need = !(f2 + mu * b2 + nu_merit * t2 <= m0 + 1e-4 * alpha * D + 1e-12 * fabs(m0)) && (++ls < 40);
         }
+        // accept the step.  Multipliers: LAMN already holds lam+ (instances that iterate) or the old values (the others), so
+        // a full step only swaps the two arrays; a shortened step (some instance of the tile) blends in place first.
         if (tid < I) {
-            sh_alpha[tid] = alpha;
-            sh_flag[tid] = active ? 1.0 : 0.0;
+            sh_alpha[tid] = active ? alpha : 0.0;
             if constexpr (C::BD) sh_az[tid] = fo.az;
         }
-        __syncthreads();
-        if (worker && sh_flag[i] != 0.0) {  // the C workers of an instance update its iterate together, loads batched
+        const bool shortened = __syncthreads_or(active && alpha != 1.0);
+        if (worker) {
             const double al = sh_alpha[i];
             constexpr int UB = 8;
-            for (int e0 = NX + j; e0 < NV; e0 += C::CB * UB) {
+            if (al != 0.0) for (int e0 = NX + j; e0 < NV; e0 += C::CB * UB) {  // the C workers of an instance update its iterate together, loads batched
                 double vz[UB], vd[UB];
                 MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) { vz[q] = Vp[(size_t)(e0 + q * C::CB) * I]; vd[q] = DVp[(size_t)(e0 + q * C::CB) * I]; }
                 MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) Vp[(size_t)(e0 + q * C::CB) * I] = fma(al, vd[q], vz[q]);
             }
-            for (int e0 = j; e0 < Mc; e0 += C::CB * UB) {
+            if (shortened) for (int e0 = j; e0 < Mc; e0 += C::CB * UB) {
                 double vl[UB], vn[UB];
-                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) { vl[q] = LAMp[(size_t)(e0 + q * C::CB) * I]; vn[q] = LAMNp[(size_t)(e0 + q * C::CB) * I]; }
-                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) LAMp[(size_t)(e0 + q * C::CB) * I] = fma(al, vn[q] - vl[q], vl[q]);
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) { vl[q] = c.LAM[(size_t)(e0 + q * C::CB) * I]; vn[q] = c.LAMN[(size_t)(e0 + q * C::CB) * I]; }
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) c.LAMN[(size_t)(e0 + q * C::CB) * I] = (al != 0.0) ? fma(al, vn[q] - vl[q], vl[q]) : vl[q];
             }
+            if (al != 0.0) {
             if constexpr (C::BD) {
                 // bound multipliers: z += alpha_z dz, then IPOPT's kappa_sigma safeguard at the new point (T1)
                 const double az = sh_az[i], mu_i = sh_mu[i];
@@ -1069,28 +1107,40 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
                     if (ub < MMPC_INF_THRESH) c.ZU[(size_t)e * I] = z_safeguard(fma(az, c.DZU[(size_t)e * I], c.ZU[(size_t)e * I]), ub - v, mu_i);
                 }
             }
+            }
         }
         __syncthreads();
+        { double* t = c.LAM; c.LAM = c.LAMN; c.LAMN = t; }
 #ifdef MMPC_T3_PROFILE
         if (it < 8) t_post[it] = clock64() - tp2;
+        if (it == 1) ts[7] = clock64();
 #endif
     }
 #ifdef MMPC_T3_PROFILE
     const long long t_loop_end = clock64();
 #endif
-    // ---- outputs: the reference's V layout, instance-major ----
-    if (valid && worker) {
-        double* Vo = io.V_out + (size_t)b * NV;
+    // ---- outputs: the reference's V layout, instance-major.  The warm start lives in LAM2: after an odd number of accepted
+    // steps the multipliers are copied back there ----
+    double* const Lcan = W.LAM2 + (size_t)tile * I * Mc + i;
+    const bool back = c.LAM != Lcan;  // tile-uniform
+    if (worker) {
+        const double* LAMp = c.LAM;
         constexpr int UB = 8;  // batched so that the loads of one batch are in flight together
-        for (int e0 = j; e0 < NV; e0 += C::CB * UB) {
-            double t[UB];
-            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) t[q] = Vp[(size_t)(e0 + q * C::CB) * I];
-            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) __stcs(&Vo[e0 + q * C::CB], t[q]);
+        if (valid) {
+            double* Vo = io.V_out + (size_t)b * NV;
+            for (int e0 = j; e0 < NV; e0 += C::CB * UB) {
+                double t[UB];
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) t[q] = Vp[(size_t)(e0 + q * C::CB) * I];
+                MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < NV) __stcs(&Vo[e0 + q * C::CB], t[q]);
+            }
         }
-        if (io.lam_out) for (int e0 = j; e0 < Mc; e0 += C::CB * UB) {
+        if ((valid && io.lam_out) || back) for (int e0 = j; e0 < Mc; e0 += C::CB * UB) {
             double t[UB];
             MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) t[q] = LAMp[(size_t)(e0 + q * C::CB) * I];
-            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) __stcs(&io.lam_out[(size_t)b * Mc + e0 + q * C::CB], t[q]);
+            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) {
+                if (valid && io.lam_out) __stcs(&io.lam_out[(size_t)b * Mc + e0 + q * C::CB], t[q]);
+                if (back) Lcan[(size_t)(e0 + q * C::CB) * I] = t[q];
+            }
         }
     }
     if (valid && tid < I && io.stats) {
@@ -1099,12 +1149,22 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
         s.ls_steps = ls_total; s.reg_steps = reg_total;
         io.stats[b] = s;
     }
+#ifdef MMPC_T3_PROFILE_CTAS
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        printf("[t3 cta] %d sm %u start %llu end %llu\n", (int)blockIdx.x, smid, gt0, gt1);
+    }
+#endif
 #ifdef MMPC_T3_PROFILE
     __syncthreads();
     if (blockIdx.x == 0 && tid == 0) {
         const long long t_end = clock64();
         printf("[t3 kernel] prologue %lld  loop %lld  epilogue %lld cycles, %d iterations\n", t_kernel0 - t_entry, t_loop_end - t_kernel0, t_end - t_loop_end, it);
-        for (int q = 0; q <= it && q < 8; ++q) printf("[t3 it %d] residuals %lld  backward %lld  forward %lld  line search + step %lld\n", q, t_res[q], t_bwd[q], t_fwd[q], t_post[q]);
+        for (int q = 0; q <= it && q < 8; ++q) printf("[t3 it %d] residuals %lld  backward %lld  forward %lld  line search + step %lld  whole iteration %lld\n", q, t_res[q], t_bwd[q], t_fwd[q], t_post[q], t_iter[q]);
+        printf("[t3 stamps it 1] top->tp0 %lld  bwd %lld  ->tg0 %lld  votes %lld  ->tp1 %lld  fwd %lld  post %lld  ->next top %lld\n", ts[1] - ts[0], ts[2] - ts[1], ts[3] - ts[2], ts[4] - ts[3], ts[5] - ts[4], ts[6] - ts[5], ts[7] - ts[6], ts[9] - ts[7]);
+        printf("[t3 glue it 1] first vote %lld  inertia loop %lld  second vote %lld\n", t_glue[0], t_glue[1], t_glue[2]);
     }
 #endif
 }
