@@ -12,6 +12,7 @@
 //
 // All arithmetic fp64 on the DFMA pipe; no tensor cores (tcgen05 has no fp64 type).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <math.h>
 

@@ -548,11 +548,15 @@ struct LaunchT2 {
     static cudaError_t run(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         using C = T2<M>;
         const size_t smem = (size_t)WARPS * C::GPW * C::GS * sizeof(double);
-        static bool attr_done = false;
-        if (!attr_done && smem > 48 * 1024) {
+        // the opt-in to more than 48 KB of dynamic shared memory is a per-device function attribute (one process may drive
+        // several GPUs through several handles); set once per device, atomically because handles may solve from several threads
+        static std::atomic<unsigned long long> attr_done{0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (smem > 48 * 1024 && !((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ULL)) {
             cudaError_t e = cudaFuncSetAttribute(solve_kernel_t2<M, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            attr_done = true;
+            attr_done.fetch_or(1ULL << (dev & 63), std::memory_order_release);
         }
         const int per_cta = WARPS * C::GPW;
         const int grid = (io.b1 - io.b0 + per_cta - 1) / per_cta;

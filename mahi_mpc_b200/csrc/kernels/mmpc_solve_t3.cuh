@@ -1174,11 +1174,15 @@ struct LaunchT3 {
     template <int I_, int CB_, int CF_, int SK_ = 0, int RK_ = 0>
     static cudaError_t go(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         using C = T3<M, I_, CB_, CF_, SK_, RK_>;
-        static bool attr_done = false;
-        if (!attr_done && C::SMEM_BYTES > 48 * 1024) {
+        // the opt-in to more than 48 KB of dynamic shared memory is a per-device function attribute (one process may drive
+        // several GPUs through several handles); set once per device, atomically because handles may solve from several threads
+        static std::atomic<unsigned long long> attr_done{0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (C::SMEM_BYTES > 48 * 1024 && !((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ULL)) {
             cudaError_t e = cudaFuncSetAttribute(solve_kernel_t3<M, I_, CB_, CF_, SK_, RK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
             if (e != cudaSuccess) return e;
-            attr_done = true;
+            attr_done.fetch_or(1ULL << (dev & 63), std::memory_order_release);
         }
         const int t0 = io.b0 / C::I, t1 = (io.b1 + C::I - 1) / C::I;  // tiles touched by [b0, b1)
         const int grid = t1 - t0;
