@@ -198,12 +198,17 @@ def run_gpu(args):
     def step_resident():
         solver.solve(d_x0, d_up, d_traj, V_out=d_V, stats_out=d_st, want_lam=False)
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    barrier()
+    # the clock sampler is started BEFORE the warm-up: nvidia-smi needs ~0.1-0.3 s to deliver its first row, longer than the
+    # timed region of a short run; the warm-up keeps the GPU under load while it spins up
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 1.0:
+            step_resident()
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches = 0
     barrier()
