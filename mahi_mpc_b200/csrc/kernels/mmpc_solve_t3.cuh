@@ -1241,7 +1241,7 @@ struct LaunchT3 {
         return cudaGetLastError();
     }
     // Configurations (tile width I, backward chunk CB, forward chunk CF), measured at N = 50 (profiles/r1_t3_configs.txt):
-    //   1   8 x 4 x 4   64 threads,  41 KB, 4 CTAs/SM: lowest latency; best while the batch leaves at most two tiles per SM
+    //   1   8 x 4 x 4   64 threads,  41 KB, 4 CTAs/SM: lowest latency; best while the batch leaves at most one tile per SM (B <= 1184)
     //   2  32 x 7 x 5  256 threads, 182 KB, 1 CTA/SM: the serial warp is full (an fp64 instruction costs the same issue
     //                  slots for 8 active lanes as for 32) and 7 worker warps evaluate 7 nodes at a time; best beyond that
     // Tried and slower: 14 x 8 x 4, 16 x 4 x 4, 32 x 4 x 4, 32 x 7 x {4, 6}, 32 x 6 x {4, 5} with warp 4 idle (SK).
@@ -1249,7 +1249,7 @@ struct LaunchT3 {
     // handle.  kernel_variant = 3 + 256*k forces configuration k.
     static cudaError_t run(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         const int forced = io.variant >> 8;
-        const int cfg = forced ? forced : (W.B > 2 * 8 * 148 ? 2 : 1);
+        const int cfg = forced ? forced : (W.B > 8 * 148 ? 2 : 1);
         if (P.bounded) {
             // finite bounds: interior point (Euler / linearised steps; bounded RK4 solves stay on T1); small models only
             if constexpr (M::NX + 2 * M::NU <= 8) {

@@ -157,7 +157,7 @@ def test_solve_vs_golden(api, golden):
         assert rel(lam[0], case["lam_g"]) < 1e-6
 
 
-# 3 + 256*2 forces T3's 32-instance tile configuration (chosen automatically only for batches beyond 2368) on ragged small batches
+# 3 + 256*2 forces T3's 32-instance tile configuration (chosen automatically only for batches beyond 1184) on ragged small batches
 @pytest.mark.parametrize("variant", [1, 2, 3, 3 + 256 * 2])
 @pytest.mark.parametrize("N,B", [(1, 3), (10, 7), (25, 33), (50, 64), (100, 8), (200, 4)])
 def test_solve_vs_oracle(api, coracle, N, B, variant):
