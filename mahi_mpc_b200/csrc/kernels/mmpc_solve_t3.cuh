@@ -115,35 +115,36 @@ __device__ __forceinline__ void t3_st_evict_last(double* p, double v) {
 #define T3_FUSLOT(a) (C::SPARSE ? __popcll(C::FUM & ((1ULL << (a)) - 1ULL)) : (a))
 
 // bounded problems only: multipliers of the lower / upper bounds and their steps, in V layout like the iterate
-template <bool BD>
+template <class M, bool BD>
 struct T3CtxBounds {};
-template <>
-struct T3CtxBounds<true> {
+template <class M>
+struct T3CtxBounds<M, true> {
     double *ZL, *ZU, *DZL, *DZU;
+    double x_min[M::NX], x_max[M::NX], u_min[M::NU], u_max[M::NU];  // copies: reached through a reference, the kernel's parameter struct is read from local memory
 };
 
 template <class M, int I_, int MODE_ = 0>
-struct T3Ctx : T3CtxBounds<((MODE_ >> 1) & 1) != 0> {
+struct T3Ctx : T3CtxBounds<M, ((MODE_ >> 1) & 1) != 0> {
     static constexpr int NX = M::NX, NU = M::NU, S = NX + NU, I = I_;
-    const mmpc_problem& P;
+    double h;                     // step size; is_linear / substeps: copies of the problem constants the sweeps need
+    int is_linear, substeps;
     int N;
     double *V, *LAM, *DV, *LAMN;  // this thread's instance inside the tile arrays: element e lives at [e * I]
     double* LINp;                 // linearisation data of the instance (AoS)
     const double* traj;
     double Q[NX], R[NU], Rm[NU], uinit[NU];
-    __device__ T3Ctx(const mmpc_problem& P_) : P(P_) {}
     template <int WANT>
     __device__ __forceinline__ void step(const double* x, const double* u, const double* wq, const double* r, const double* lam,
                                          double* F, double* Fx, double* Fu, double* Hs) const {
-        if (P.is_linear) {
+        if (is_linear) {
             double x0[NX];
             MMPC_UNROLL for (int i = 0; i < NX; ++i) x0[i] = V[(size_t)i * I];
-            step_linear<M, WANT>(P.h, x, u, LINp, LINp + NX * NX, LINp + NX * NX + NX * NU, x0, uinit, F, Fx, Fu, Hs);
+            step_linear<M, WANT>(h, x, u, LINp, LINp + NX * NX, LINp + NX * NX + NX * NU, x0, uinit, F, Fx, Fu, Hs);
         } else if (MODE_ & 1) {
-            step_rk4<M, (WANT >= 1 ? 1 : 0)>(P.h, P.substeps, x, u, F, Fx, Fu);
+            step_rk4<M, (WANT >= 1 ? 1 : 0)>(h, substeps, x, u, F, Fx, Fu);
             if (WANT >= 2) MMPC_UNROLL for (int i = 0; i < S * (S + 1) / 2; ++i) Hs[i] = 0.0;  // Gauss-Newton Hessian under RK4
         } else {
-            step_euler<M, WANT>(P.h, x, u, wq, r, lam, F, Fx, Fu, Hs);
+            step_euler<M, WANT>(h, x, u, wq, r, lam, F, Fx, Fu, Hs);
         }
     }
 };
@@ -191,11 +192,11 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I, C::MODE>& c, i
         const double* zl = c.ZL + (size_t)k * S * I;
         const double* zu = c.ZU + (size_t)k * S * I;
         MMPC_UNROLL for (int a = 0; a < NU; ++a) {
-            const BoundTerm t = bound_term(u[a], c.P.u_min[a], c.P.u_max[a], zl[(NX + a) * I], zu[(NX + a) * I], mu, unused);
+            const BoundTerm t = bound_term(u[a], c.u_min[a], c.u_max[a], zl[(NX + a) * I], zu[(NX + a) * I], mu, unused);
             sgu[a] = t.sigma; gpu_[a] = t.gphi;
         }
         MMPC_UNROLL for (int a = 0; a < NX; ++a) {
-            const BoundTerm t = bound_term(xn[a], c.P.x_min[a], c.P.x_max[a], zl[(S + a) * I], zu[(S + a) * I], mu, unused);
+            const BoundTerm t = bound_term(xn[a], c.x_min[a], c.x_max[a], zl[(S + a) * I], zu[(S + a) * I], mu, unused);
             sgn[a] = t.sigma; gpn[a] = t.gphi;
         }
     }
@@ -569,7 +570,7 @@ __device__ __noinline__ void t3_residuals(const T3Ctx<M, C::I, C::MODE>& cin, do
                 n.theta += fabs(cr);
                 n.lam_l1 += fabs(lam[a]);
                 double dres_n = 0.0;
-                if constexpr (C::BD != 0) { dres_n = bound_term(xn[a], c.P.x_min[a], c.P.x_max[a], zln[a], zun[a], 0.0, n).dres; }
+                if constexpr (C::BD != 0) { dres_n = bound_term(xn[a], c.x_min[a], c.x_max[a], zln[a], zun[a], 0.0, n).dres; }
                 if (k == N - 1) n.dual_inf = fmax(n.dual_inf, C::BD ? fabs(-lam[a] + dres_n) : fabs(lam[a]));  // stationarity w.r.t. x_N
             }
             MMPC_UNROLL for (int a = 0; a < NX; ++a) {
@@ -580,7 +581,7 @@ __device__ __noinline__ void t3_residuals(const T3Ctx<M, C::I, C::MODE>& cin, do
                 }
                 if (k) {
                     if constexpr (C::BD != 0) {
-                        const BoundTerm tx = bound_term(x[a], c.P.x_min[a], c.P.x_max[a], zlx[a], zux[a], 0.0, own);
+                        const BoundTerm tx = bound_term(x[a], c.x_min[a], c.x_max[a], zlx[a], zux[a], 0.0, own);
                         n.dual_inf = fmax(n.dual_inf, fabs(g + l - lam_prev[a] + tx.dres));
                     } else {
                         n.dual_inf = fmax(n.dual_inf, fabs(g + l - lam_prev[a]));
@@ -599,7 +600,7 @@ __device__ __noinline__ void t3_residuals(const T3Ctx<M, C::I, C::MODE>& cin, do
                 n.fval = fma(c.Rm[a] * u[a], u[a], n.fval);
                 const double qu = g + dRu + 2.0 * c.Rm[a] * u[a];
                 if constexpr (C::BD != 0) {
-                    const BoundTerm tu = bound_term(u[a], c.P.u_min[a], c.P.u_max[a], zlu[a], zuu[a], 0.0, n);
+                    const BoundTerm tu = bound_term(u[a], c.u_min[a], c.u_max[a], zlu[a], zuu[a], 0.0, n);
                     n.dual_inf = fmax(n.dual_inf, fabs(qu + l - dRn + tu.dres));
                 } else {
                     n.dual_inf = fmax(n.dual_inf, fabs(qu + l - dRn));
@@ -646,6 +647,19 @@ __device__ __forceinline__ void t3_trial_node(const T3Ctx<M, C::I, C::MODE>& c, 
     const double* d = c.DV + (size_t)k * S * I;
     double x[NX], u[NU], v[NU], xn[NX], F[NX], r[NX];
     MMPC_UNROLL for (int a = 0; a < NX; ++a) r[a] = c.traj[(size_t)k * NX + a];  // with the other loads: one L2 round trip, not two
+    // bounded, full step: the bound multipliers of u_k and x_{k+1}, loaded with everything else (one L2 round trip)
+    double zlq[NX + NU], zuq[NX + NU];
+    if constexpr (C::BD != 0) {
+        if (bd.full) {
+            const double* zl = c.ZL + ((size_t)k * S + NX) * I;
+            const double* zu = c.ZU + ((size_t)k * S + NX) * I;
+            MMPC_UNROLL for (int q = 0; q < S; ++q) {  // q < NU: u_k; q >= NU: x_{k+1}
+                const double lb = q < NU ? c.u_min[q] : c.x_min[q - NU], ub = q < NU ? c.u_max[q] : c.x_max[q - NU];
+                zlq[q] = lb > -MMPC_INF_THRESH ? zl[q * I] : 0.0;
+                zuq[q] = ub < MMPC_INF_THRESH ? zu[q * I] : 0.0;
+            }
+        }
+    }
     if (keep_lam) {  // forward sweep, instance that no longer iterates: LAMN must hold its multipliers when LAM and LAMN swap
         double lk[NX];
         MMPC_UNROLL for (int a = 0; a < NX; ++a) lk[a] = c.LAM[((size_t)k * NX + a) * I];
@@ -674,24 +688,24 @@ __device__ __forceinline__ void t3_trial_node(const T3Ctx<M, C::I, C::MODE>& c, 
         if (bd.full) {  // alpha = 1: u, xn are z + dz; bound_step wants the iterate and the step
             FwdOut o;
             o.amax = bd.amax; o.az = bd.az; o.bar1 = bd.bar1;
-            const double* zl = c.ZL + (size_t)k * S * I;
-            const double* zu = c.ZU + (size_t)k * S * I;
             double* dzl = c.DZL + (size_t)k * S * I;
             double* dzu = c.DZU + (size_t)k * S * I;
             MMPC_UNROLL for (int a = 0; a < NU; ++a) {
                 double dl, du_;
-                bound_step(z[(NX + a) * I], d[(NX + a) * I], c.P.u_min[a], c.P.u_max[a], zl[(NX + a) * I], zu[(NX + a) * I], bd.mu, bd.tau, dl, du_, o);
-                dzl[(NX + a) * I] = dl; dzu[(NX + a) * I] = du_;
+                bound_step(z[(NX + a) * I], d[(NX + a) * I], c.u_min[a], c.u_max[a], zlq[a], zuq[a], bd.mu, bd.tau, dl, du_, o);
+                if (c.u_min[a] > -MMPC_INF_THRESH) dzl[(NX + a) * I] = dl;
+                if (c.u_max[a] < MMPC_INF_THRESH) dzu[(NX + a) * I] = du_;
             }
             MMPC_UNROLL for (int a = 0; a < NX; ++a) {
                 double dl, du_;
-                bound_step(z[(S + a) * I], d[(S + a) * I], c.P.x_min[a], c.P.x_max[a], zl[(S + a) * I], zu[(S + a) * I], bd.mu, bd.tau, dl, du_, o);
-                dzl[(S + a) * I] = dl; dzu[(S + a) * I] = du_;
+                bound_step(z[(S + a) * I], d[(S + a) * I], c.x_min[a], c.x_max[a], zlq[NU + a], zuq[NU + a], bd.mu, bd.tau, dl, du_, o);
+                if (c.x_min[a] > -MMPC_INF_THRESH) dzl[(S + a) * I] = dl;
+                if (c.x_max[a] < MMPC_INF_THRESH) dzu[(S + a) * I] = du_;
             }
             bd.amax = o.amax; bd.az = o.az; bd.bar1 = o.bar1;
         } else {
-            MMPC_UNROLL for (int a = 0; a < NU; ++a) bd.bar1 += barrier_of(u[a], c.P.u_min[a], c.P.u_max[a]);
-            MMPC_UNROLL for (int a = 0; a < NX; ++a) bd.bar1 += barrier_of(xn[a], c.P.x_min[a], c.P.x_max[a]);
+            MMPC_UNROLL for (int a = 0; a < NU; ++a) bd.bar1 += barrier_of(u[a], c.u_min[a], c.u_max[a]);
+            MMPC_UNROLL for (int a = 0; a < NX; ++a) bd.bar1 += barrier_of(xn[a], c.x_min[a], c.x_max[a]);
         }
     }
 }
@@ -897,13 +911,16 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
     const bool valid = b >= io.b0 && b < io.b1;
     const int bi = valid ? b : io.b1 - 1;       // surplus slots read the last instance's inputs and never write outputs
 
-    T3Ctx<M, I, C::MODE> c(P);
+    T3Ctx<M, I, C::MODE> c;
     c.N = N;
+    c.h = P.h; c.is_linear = P.is_linear; c.substeps = P.substeps;
     // the iterate lives tile-wise, [element][instance]: every access of a warp is a run of full sectors whatever I is
     c.V = W.V2 + (size_t)tile * I * NV + i; c.LAM = W.LAM2 + (size_t)tile * I * Mc + i;
     c.DV = W.DV2 + (size_t)tile * I * NV + i; c.LAMN = W.LAMN2 + (size_t)tile * I * Mc + i;
     c.LINp = W.LIN2 + (size_t)b * C::LIN;
     if constexpr (C::BD != 0) {
+        MMPC_UNROLL for (int a = 0; a < NX; ++a) { c.x_min[a] = P.x_min[a]; c.x_max[a] = P.x_max[a]; }
+        MMPC_UNROLL for (int a = 0; a < NU; ++a) { c.u_min[a] = P.u_min[a]; c.u_max[a] = P.u_max[a]; }
         c.ZL = W.ZL2 + (size_t)tile * I * NV + i; c.ZU = W.ZU2 + (size_t)tile * I * NV + i;
         c.DZL = W.DZL2 + (size_t)tile * I * NV + i; c.DZU = W.DZU2 + (size_t)tile * I * NV + i;
     }
@@ -1137,18 +1154,30 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
                 MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) { vl[q] = c.LAM[(size_t)(e0 + q * C::CB) * I]; vn[q] = c.LAMN[(size_t)(e0 + q * C::CB) * I]; }
                 MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * C::CB < Mc) c.LAMN[(size_t)(e0 + q * C::CB) * I] = (al != 0.0) ? fma(al, vn[q] - vl[q], vl[q]) : vl[q];
             }
-            if (al != 0.0) {
-            if constexpr (C::BD) {
-                // bound multipliers: z += alpha_z dz, then IPOPT's kappa_sigma safeguard at the new point (T1)
+        }
+        if constexpr (C::BD != 0) {
+            // bound multipliers: z += alpha_z dz, then IPOPT's kappa_sigma safeguard at the new point (T1).  Node by node, so
+            // that the loads of one node are in flight together; only variables with a finite bound are touched.
+            __syncthreads();  // the iterate above was updated element-wise by other threads of the instance
+            if (worker && sh_alpha[i] != 0.0) {
                 const double az = sh_az[i], mu_i = sh_mu[i];
-                for (int e = NX + j; e < NV; e += C::CB) {
-                    const int r = e % S;
-                    const double lb = r < NX ? P.x_min[r] : P.u_min[r - NX], ub = r < NX ? P.x_max[r] : P.u_max[r - NX];
-                    const double v = Vp[(size_t)e * I];  // the updated value (this thread wrote it above)
-                    if (lb > -MMPC_INF_THRESH) c.ZL[(size_t)e * I] = z_safeguard(fma(az, c.DZL[(size_t)e * I], c.ZL[(size_t)e * I]), v - lb, mu_i);
-                    if (ub < MMPC_INF_THRESH) c.ZU[(size_t)e * I] = z_safeguard(fma(az, c.DZU[(size_t)e * I], c.ZU[(size_t)e * I]), ub - v, mu_i);
+                for (int k = j; k < N; k += C::CB) {
+                    // q < NU: u_k, element k S + NX + q;  q >= NU: x_{k+1}, element (k+1) S + (q - NU) = k S + NX + q as well
+                    double v[S], zl[S], zu[S], dl[S], du[S];
+                    MMPC_UNROLL for (int q = 0; q < S; ++q) {
+                        const double lb = q < NU ? P.u_min[q] : P.x_min[q - NU], ub = q < NU ? P.u_max[q] : P.x_max[q - NU];
+                        const size_t e = ((size_t)k * S + NX + q) * I;
+                        if (lb > -MMPC_INF_THRESH || ub < MMPC_INF_THRESH) v[q] = c.V[e];
+                        if (lb > -MMPC_INF_THRESH) { zl[q] = c.ZL[e]; dl[q] = c.DZL[e]; }
+                        if (ub < MMPC_INF_THRESH) { zu[q] = c.ZU[e]; du[q] = c.DZU[e]; }
+                    }
+                    MMPC_UNROLL for (int q = 0; q < S; ++q) {
+                        const double lb = q < NU ? P.u_min[q] : P.x_min[q - NU], ub = q < NU ? P.u_max[q] : P.x_max[q - NU];
+                        const size_t e = ((size_t)k * S + NX + q) * I;
+                        if (lb > -MMPC_INF_THRESH) c.ZL[e] = z_safeguard(fma(az, dl[q], zl[q]), v[q] - lb, mu_i);
+                        if (ub < MMPC_INF_THRESH) c.ZU[e] = z_safeguard(fma(az, du[q], zu[q]), ub - v[q], mu_i);
+                    }
                 }
-            }
             }
         }
         __syncthreads();
