@@ -633,12 +633,30 @@ __device__ __noinline__ void t3_residuals(const T3Ctx<M, C::I, C::MODE>& cin, do
 }
 
 // merit pieces of node k at z + alpha dz
-// bounded problems: barrier of the trial point and, for the full step of the forward sweep (full = true), the multiplier
-// steps and the fraction-to-the-boundary limits (T1's bound_step)
+// bounded problems: barrier of the trial point (full = false: merit passes, t3_trial) or, in the forward sweep (full = true),
+// the multiplier steps and the fraction-to-the-boundary limits only -- the merit of a bounded problem is evaluated at
+// alpha = alpha_max by one t3_trial pass after the sweep, so the sweep itself needs neither the model nor the logarithms
 struct T3TrialBD {
     double bar1, amax, az, mu, tau;
     bool full;
 };
+// T1's bound_step without the barrier of the full step
+__device__ __forceinline__ void t3_bound_step(double v, double d, double lb, double ub, double zl, double zu, double mu, double tau, double& dzl,
+                                              double& dzu, double& amax, double& az) {
+    dzl = 0.0; dzu = 0.0;
+    if (lb > -MMPC_INF_THRESH) {
+        const double s = v - lb;
+        dzl = (mu - zl * d) / s - zl;
+        if (d < 0.0) amax = fmin(amax, -tau * s / d);
+        if (dzl < 0.0) az = fmin(az, -tau * zl / dzl);
+    }
+    if (ub < MMPC_INF_THRESH) {
+        const double s = ub - v;
+        dzu = (mu + zu * d) / s - zu;
+        if (d > 0.0) amax = fmin(amax, tau * s / d);
+        if (dzu < 0.0) az = fmin(az, -tau * zu / dzu);
+    }
+}
 template <class M, class C>
 __device__ __forceinline__ void t3_trial_node(const T3Ctx<M, C::I, C::MODE>& c, int k, double alpha, double& f1, double& th1, T3TrialBD& bd,
                                               bool keep_lam = false) {
@@ -673,36 +691,35 @@ __device__ __forceinline__ void t3_trial_node(const T3Ctx<M, C::I, C::MODE>& c, 
         u[a] = fma(alpha, d[(NX + a) * I], z[(NX + a) * I]);
         v[a] = k ? fma(alpha, d[(NX + a - S) * I], z[(NX + a - S) * I]) : c.uinit[a];
     }
-    c.template step<0>(x, u, nullptr, nullptr, nullptr, F, nullptr, nullptr, nullptr);
-    MMPC_UNROLL for (int a = 0; a < NX; ++a) {
-        const double e = F[a] - r[a];
-        f1 = fma(c.Q[a] * e, e, f1);
-        th1 += fabs(F[a] - xn[a]);
-    }
-    MMPC_UNROLL for (int a = 0; a < NU; ++a) {
-        const double dd = u[a] - v[a];
-        f1 = fma(c.R[a] * dd, dd, f1);
-        f1 = fma(c.Rm[a] * u[a], u[a], f1);
+    if (!(C::BD && bd.full)) {
+        c.template step<0>(x, u, nullptr, nullptr, nullptr, F, nullptr, nullptr, nullptr);
+        MMPC_UNROLL for (int a = 0; a < NX; ++a) {
+            const double e = F[a] - r[a];
+            f1 = fma(c.Q[a] * e, e, f1);
+            th1 += fabs(F[a] - xn[a]);
+        }
+        MMPC_UNROLL for (int a = 0; a < NU; ++a) {
+            const double dd = u[a] - v[a];
+            f1 = fma(c.R[a] * dd, dd, f1);
+            f1 = fma(c.Rm[a] * u[a], u[a], f1);
+        }
     }
     if constexpr (C::BD) {
-        if (bd.full) {  // alpha = 1: u, xn are z + dz; bound_step wants the iterate and the step
-            FwdOut o;
-            o.amax = bd.amax; o.az = bd.az; o.bar1 = bd.bar1;
+        if (bd.full) {  // multiplier steps and step-length limits from the iterate and the step
             double* dzl = c.DZL + (size_t)k * S * I;
             double* dzu = c.DZU + (size_t)k * S * I;
             MMPC_UNROLL for (int a = 0; a < NU; ++a) {
                 double dl, du_;
-                bound_step(z[(NX + a) * I], d[(NX + a) * I], c.u_min[a], c.u_max[a], zlq[a], zuq[a], bd.mu, bd.tau, dl, du_, o);
+                t3_bound_step(z[(NX + a) * I], d[(NX + a) * I], c.u_min[a], c.u_max[a], zlq[a], zuq[a], bd.mu, bd.tau, dl, du_, bd.amax, bd.az);
                 if (c.u_min[a] > -MMPC_INF_THRESH) dzl[(NX + a) * I] = dl;
                 if (c.u_max[a] < MMPC_INF_THRESH) dzu[(NX + a) * I] = du_;
             }
             MMPC_UNROLL for (int a = 0; a < NX; ++a) {
                 double dl, du_;
-                bound_step(z[(S + a) * I], d[(S + a) * I], c.x_min[a], c.x_max[a], zlq[NU + a], zuq[NU + a], bd.mu, bd.tau, dl, du_, o);
+                t3_bound_step(z[(S + a) * I], d[(S + a) * I], c.x_min[a], c.x_max[a], zlq[NU + a], zuq[NU + a], bd.mu, bd.tau, dl, du_, bd.amax, bd.az);
                 if (c.x_min[a] > -MMPC_INF_THRESH) dzl[(S + a) * I] = dl;
                 if (c.x_max[a] < MMPC_INF_THRESH) dzu[(S + a) * I] = du_;
             }
-            bd.amax = o.amax; bd.az = o.az; bd.bar1 = o.bar1;
         } else {
             MMPC_UNROLL for (int a = 0; a < NU; ++a) bd.bar1 += barrier_of(u[a], c.u_min[a], c.u_max[a]);
             MMPC_UNROLL for (int a = 0; a < NX; ++a) bd.bar1 += barrier_of(xn[a], c.x_min[a], c.x_max[a]);
@@ -1119,11 +1136,10 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
         double f1 = fo.f1, th1 = fo.th1, bar1 = fo.bar1;
         int ls = 0;
         if constexpr (C::BD) {
-            if (__syncthreads_or(active && alpha < 1.0)) {  // the merit terms of the forward sweep are those of alpha = 1
-                if (tid < I) sh_alpha[tid] = alpha;
-                __syncthreads();
-                t3_trial<M, C>(c, smem, tid, f1, th1, bar1);
-            }
+            // the forward sweep of a bounded problem computes no merit terms (alpha_max is known only when it ends)
+            if (tid < I) sh_alpha[tid] = alpha;
+            __syncthreads();
+            t3_trial<M, C>(c, smem, tid, f1, th1, bar1);
         }
         bool need = active && !(f1 + mu * bar1 + nu_merit * th1 <= m0 + 1e-4 * alpha * D + 1e-12 * fabs(m0));
         while (__syncthreads_or(need)) {
