@@ -67,16 +67,18 @@ struct BoundTerm {
 };
 __device__ __forceinline__ BoundTerm bound_term(double v, double lb, double ub, double zl, double zu, double mu, SweepNorms& n) {
     BoundTerm t{0.0, 0.0, 0.0};
+    double sprod = 1.0;  // product of the slacks: one logarithm per variable (see barrier_of)
     if (lb > -MMPC_INF_THRESH) {
         const double s = v - lb;
         t.sigma += zl / s; t.gphi -= mu / s; t.dres -= zl;
-        n.z_l1 += fabs(zl); n.cmax = fmax(n.cmax, s * zl); n.cmin = fmin(n.cmin, s * zl); n.barrier -= log(s);
+        n.z_l1 += fabs(zl); n.cmax = fmax(n.cmax, s * zl); n.cmin = fmin(n.cmin, s * zl); sprod *= s;
     }
     if (ub < MMPC_INF_THRESH) {
         const double s = ub - v;
         t.sigma += zu / s; t.gphi += mu / s; t.dres += zu;
-        n.z_l1 += fabs(zu); n.cmax = fmax(n.cmax, s * zu); n.cmin = fmin(n.cmin, s * zu); n.barrier -= log(s);
+        n.z_l1 += fabs(zu); n.cmax = fmax(n.cmax, s * zu); n.cmin = fmin(n.cmin, s * zu); sprod *= s;
     }
+    if (lb > -MMPC_INF_THRESH || ub < MMPC_INF_THRESH) n.barrier -= log(sprod);
     return t;
 }
 
@@ -328,10 +330,12 @@ __device__ __forceinline__ void bound_step(double v, double d, double lb, double
     }
 }
 __device__ __forceinline__ double barrier_of(double v, double lb, double ub) {
-    double b = 0.0;
-    if (lb > -MMPC_INF_THRESH) b -= log(fmax(v - lb, 1e-300));
-    if (ub < MMPC_INF_THRESH) b -= log(fmax(ub - v, 1e-300));
-    return b;
+    const bool hl = lb > -MMPC_INF_THRESH, hu = ub < MMPC_INF_THRESH;
+    // a two-sided bound takes one logarithm: -log(sl) - log(su) = -log(sl su) (the slacks are far from the under/overflow range)
+    if (hl && hu) return -log(fmax(v - lb, 1e-300) * fmax(ub - v, 1e-300));
+    if (hl) return -log(fmax(v - lb, 1e-300));
+    if (hu) return -log(fmax(ub - v, 1e-300));
+    return 0.0;
 }
 
 // forward sweep: step, new multipliers, directional derivative of the (barrier) objective, and -- fused -- the
