@@ -3,7 +3,9 @@
 // the same ModelParameters / ModelGenerator calls.  Output in the working directory:
 //   <name>.json, <name>.cu -> <name>.so (CUDA kernels, sm_100a), <name>_linear_functions.c -> .so (CPU, CasADi ABI)
 // where <name> = nonlinear_double_pendulum, or linear_double_pendulum with -l / --linear.
-//   usage: ex_model_generate [-l] [-n NODES] [-d STEP_MS]
+//   usage: ex_model_generate [-l] [-n NODES] [-d STEP_MS] [--name NAME]
+// --name overrides <name>: the reference's control drivers load "double_pendulum" / "linear_double_pendulum"
+// (examples/model_control_example.cpp:17-18), not the names its generate driver writes.
 #include <Mahi/Mpc/ModelGenerator.hpp>
 #include <Mahi/Util.hpp>
 
@@ -40,7 +42,7 @@ Pendulum double_pendulum(double L, double m, double g) {
 int main(int argc, char* argv[]) {
     mahi::util::Options options("ex_model_generate", "Generates the double-pendulum MPC model for mahi-mpc-b200");
     options.add_options()("l,linear", "Generates linearized model.")("n,nodes", "number of shooting nodes (default 25)", true)(
-        "d,dt", "step size in milliseconds (default 2)", true)("h,help", "print help");
+        "d,dt", "step size in milliseconds (default 2)", true)("name", "model name (default [non]linear_double_pendulum)", true)("h,help", "print help");
     auto result = options.parse(argc, argv);
     if (result.count("help")) {
         std::cout << options.help();
@@ -51,7 +53,7 @@ int main(int argc, char* argv[]) {
     const mahi::util::Time time_step = mahi::util::milliseconds(result.count("dt") ? std::stoi(result.values("dt")[0]) : 2);
 
     const Pendulum pend = double_pendulum(1.0, 1.0, 9.81);
-    const std::string model_name = std::string(linear ? "linear_" : "nonlinear_") + "double_pendulum";
+    const std::string model_name = result.count("name") ? result.values("name")[0] : std::string(linear ? "linear_" : "nonlinear_") + "double_pendulum";
 
     ModelParameters model_parameters(model_name, pend.x.size1(), pend.u.size1(), time_step, num_shooting_nodes, linear);
     ModelGenerator my_generator(model_parameters, pend.x, pend.x_dot, pend.u);

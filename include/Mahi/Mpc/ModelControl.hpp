@@ -51,9 +51,13 @@ public:
     void update_weights(std::vector<double> Q = {}, std::vector<double> R = {}, std::vector<double> Rm = {});
     void update_control_limits(std::vector<double> u_min, std::vector<double> u_max);
 
-    SolveInfo last_solve_info() const { return m_info; }
-    /// the full decision vector V of the last solve, reference layout (ModelGenerator.cpp:76-112)
-    const std::vector<double>& last_solution() const { return m_V; }
+    SolveInfo last_solve_info() const { std::lock_guard<std::mutex> lg(m_output_mutex); return m_info; }
+    /// the full decision vector V of the last solve, reference layout (ModelGenerator.cpp:76-112); a copy, because the
+    /// solver thread of start_calc() overwrites it every cycle
+    std::vector<double> last_solution() const { std::lock_guard<std::mutex> lg(m_output_mutex); return m_V_out; }
+    /// message of the exception that stopped the start_calc() thread, empty if it is healthy (the reference's thread
+    /// would have called std::terminate)
+    std::string worker_error() const { std::lock_guard<std::mutex> lg(m_output_mutex); return m_worker_error; }
 
 private:
     void format_outputs(const std::vector<double>& opt_output);
@@ -63,7 +67,8 @@ private:
     mahi::util::Time curr_time;
     mmpc_model* m_model = nullptr;
     mmpc_solver* m_solver = nullptr;
-    std::vector<double> m_Q, m_R, m_Rm, m_V;
+    std::vector<double> m_Q, m_R, m_Rm, m_V, m_V_out;
+    std::string m_worker_error;
     bool m_weights_dirty = true, m_limits_dirty = false;
     SolveInfo m_info;
 
@@ -71,7 +76,7 @@ private:
     std::thread m_worker;
     mahi::util::Time m_time;
     std::vector<double> m_state, m_control, m_traj;
-    std::mutex m_state_mutex, m_output_mutex, m_control_limits_mutex, m_weights_mutex;
+    mutable std::mutex m_state_mutex, m_output_mutex, m_control_limits_mutex, m_weights_mutex;
 };
 
 /// B independent ModelControl::calc_u problems per call (one kernel launch); instance-major flat vectors.

@@ -20,7 +20,9 @@ public:
     ~ModelGenerator();
     void create_model();
     void generate_c_code();
-    void generate_linear_functions();
+    /// emits + compiles <name>_linear_functions.so from the three symbolic functions (reference signature,
+    /// ModelGenerator.hpp:27; create_model() calls it with jacobian(x_dot, x), jacobian(x_dot, u) and x_dot)
+    void generate_linear_functions(casadi::Function get_A, casadi::Function get_B, casadi::Function get_x_dot_init);
     void compile_model();
     void save_param_file();
 

@@ -33,6 +33,11 @@ struct TrajectoryParameters {  // declared by the reference, unused by the libra
     int num_x_t = 0, num_u_t = 0, num_shooting_nodes_t = 0;
 };
 
+/// nlohmann-style (de)serialisation hooks, found by ADL from mahi::util::json (reference: ModelParameters.hpp:43-45,
+/// ModelParameters.cpp:37-72): `j["model"] = params;` and `j["model"].get<ModelParameters>()`.
+void to_json(mahi::util::json& j, const ModelParameters& p);
+void from_json(const mahi::util::json& j, ModelParameters& p);
+
 /// {"model": {...}} text in the reference's schema; times in microseconds.
 std::string to_json_string(const ModelParameters& p);
 /// Parses the text produced by to_json_string / by the reference (nlohmann). Throws std::runtime_error.

@@ -1,13 +1,17 @@
 // mahi-mpc-b200 :: the slice of mahi::util the MPC library and its drivers use (the real mahi-util is
 // FetchContent'ed unpinned by the reference, CMakeLists.txt:42, and is not available offline).
-// Surface: Time + seconds/milliseconds/microseconds, Clock, Timer, sleep, PI, mean, print,
-// Options (cxxopts-style flags used by the example drivers).
+// Surface: Time + seconds/milliseconds/microseconds, Clock, Timer, Timestamp, sleep, PI, mean, print,
+// json (Mahi/Util/Json.hpp), Options (cxxopts-style flags incl. value<T>() / result["x"].as<T>() as used by
+// examples/thread_model_control_example.cpp:13-28), stream output of std::vector (examples/model_control_example.cpp:104).
 #pragma once
 #include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <ctime>
+#include <fstream>
 #include <iostream>
+#include <memory>
 #include <map>
 #include <numeric>
 #include <sstream>
@@ -15,6 +19,17 @@
 #include <string>
 #include <thread>
 #include <vector>
+
+#include <Mahi/Util/Json.hpp>
+
+/// `file << std::vector<T>` as the reference's drivers write it (mahi-util provides this overload at global scope);
+/// prints "[a, b, c]" -- valid MATLAB, which is what the drivers emit.
+template <class T>
+std::ostream& operator<<(std::ostream& os, const std::vector<T>& v) {
+    os << "[";
+    for (size_t i = 0; i < v.size(); ++i) os << (i ? ", " : "") << v[i];
+    return os << "]";
+}
 
 namespace mahi {
 namespace util {
@@ -52,6 +67,31 @@ public:
     Time restart() { Time t = get_elapsed_time(); m_t0 = std::chrono::steady_clock::now(); return t; }
 private:
     std::chrono::steady_clock::time_point m_t0;
+};
+
+/// Wall-clock time stamp (mahi::util::Timestamp look-alike; the drivers print ts.hh_mm_ss_mmm() into their result files).
+class Timestamp {
+public:
+    Timestamp() {
+        const auto now = std::chrono::system_clock::now();
+        const std::time_t t = std::chrono::system_clock::to_time_t(now);
+        std::tm tmv{};
+        localtime_r(&t, &tmv);
+        year = tmv.tm_year + 1900; month = tmv.tm_mon + 1; yday = tmv.tm_yday; mday = tmv.tm_mday; wday = tmv.tm_wday;
+        hour = tmv.tm_hour; min = tmv.tm_min; sec = tmv.tm_sec;
+        millis = static_cast<int>(std::chrono::duration_cast<std::chrono::milliseconds>(now.time_since_epoch()).count() % 1000);
+    }
+    std::string yyyy_mm_dd() const { return fmt("%04d-%02d-%02d", year, month, mday); }
+    std::string hh_mm_ss() const { return fmt("%02d:%02d:%02d", hour, min, sec); }
+    std::string hh_mm_ss_mmm() const { return hh_mm_ss() + fmt(".%03d", millis, 0, 0); }
+    std::string yyyy_mm_dd_hh_mm_ss() const { return yyyy_mm_dd() + "_" + hh_mm_ss(); }
+    int year, month, yday, mday, wday, hour, min, sec, millis;
+private:
+    static std::string fmt(const char* f, int a, int b, int c) {
+        char buf[48];
+        std::snprintf(buf, sizeof buf, f, a, b, c);
+        return buf;
+    }
 };
 
 inline void sleep(Time t) { std::this_thread::sleep_for(std::chrono::microseconds(t.as_microseconds())); }
@@ -110,15 +150,53 @@ void print(const std::string& f, const A&... args) {
     std::cout << os.str() << std::endl;
 }
 
-/// Minimal command-line flags in the style of mahi::util::Options (cxxopts): "s,long" names, count(), values.
+/// value<T>() marks an option that takes an argument of type T (cxxopts spelling)
+struct ValueSpec {};
+template <class T>
+std::shared_ptr<ValueSpec> value() { return std::make_shared<ValueSpec>(); }
+
+/// Minimal command-line flags in the style of mahi::util::Options (cxxopts): "s,long" names, count(), values,
+/// result["name"].as<T>() for T = arithmetic, std::string, std::vector<arithmetic> (comma separated and/or repeated).
 class Options {
 public:
+    class OptionValue {
+    public:
+        explicit OptionValue(std::vector<std::string> raw) : m_raw(std::move(raw)) {}
+        size_t count() const { return m_raw.size(); }
+        template <class T>
+        T as() const { T out{}; convert(out); return out; }
+    private:
+        static void parse_one(const std::string& s, std::string& out) { out = s; }
+        static void parse_one(const std::string& s, bool& out) { out = !(s == "0" || s == "false" || s == "False"); }
+        template <class T>
+        static typename std::enable_if<std::is_arithmetic<T>::value>::type parse_one(const std::string& s, T& out) {
+            std::stringstream ss(s);
+            double d = 0;
+            if (!(ss >> d)) throw std::invalid_argument("option value '" + s + "' is not a number");
+            out = static_cast<T>(d);
+        }
+        template <class T>
+        void convert(T& out) const {
+            if (m_raw.empty()) throw std::domain_error("option has no value");
+            parse_one(m_raw.back(), out);
+        }
+        template <class T>
+        void convert(std::vector<T>& out) const {
+            for (const auto& s : m_raw) {
+                std::stringstream ss(s);
+                std::string tok;
+                while (std::getline(ss, tok, ',')) if (!tok.empty()) { T v{}; parse_one(tok, v); out.push_back(v); }
+            }
+        }
+        std::vector<std::string> m_raw;
+    };
     class Result {
     public:
-        size_t count(const std::string& name) const { auto it = m_vals.find(name); return it == m_vals.end() ? 0 : it->second.size(); }
+        OptionValue operator[](const std::string& name) const { return OptionValue(values(name)); }
+        size_t count(const std::string& name) const { auto it = m_vals.find(key(name)); return it == m_vals.end() ? 0 : it->second.size(); }
         const std::vector<std::string>& values(const std::string& name) const {
             static const std::vector<std::string> none;
-            auto it = m_vals.find(name);
+            auto it = m_vals.find(key(name));
             return it == m_vals.end() ? none : it->second;
         }
         std::vector<double> doubles(const std::string& name) const {
@@ -132,13 +210,19 @@ public:
         }
     private:
         friend class Options;
+        const std::string& key(const std::string& name) const { auto it = m_short.find(name); return it == m_short.end() ? name : it->second; }
         std::map<std::string, std::vector<std::string>> m_vals;
+        std::map<std::string, std::string> m_short;  // short name -> long name: count("m") == count("ma27")
     };
     class Adder {
     public:
         explicit Adder(Options& o) : m_o(o) {}
         Adder& operator()(const std::string& names, const std::string& desc, bool takes_value = false) {
             m_o.add(names, desc, takes_value);
+            return *this;
+        }
+        Adder& operator()(const std::string& names, const std::string& desc, const std::shared_ptr<ValueSpec>&) {
+            m_o.add(names, desc, true);
             return *this;
         }
     private:
@@ -148,6 +232,7 @@ public:
     Adder add_options() { return Adder(*this); }
     Result parse(int argc, char* argv[]) const {
         Result r;
+        r.m_short = m_short;
         for (int i = 1; i < argc; ++i) {
             std::string a = argv[i];
             std::string key;
@@ -175,6 +260,11 @@ private:
         std::string s, l = names;
         const size_t c = names.find(',');
         if (c != std::string::npos) { s = names.substr(0, c); l = names.substr(c + 1); }
+        auto trim = [](std::string& t) {  // the reference writes "q, q_vec" (thread_model_control_example.cpp:16)
+            while (!t.empty() && t.front() == ' ') t.erase(t.begin());
+            while (!t.empty() && t.back() == ' ') t.pop_back();
+        };
+        trim(s); trim(l);
         if (!s.empty()) m_short[s] = l;
         m_takes[l] = takes_value;
         m_desc.push_back((s.empty() ? "" : "-" + s + ", ") + "--" + l + "  " + desc);

@@ -71,14 +71,30 @@ private:
     std::vector<double> m_d;
 };
 
-/// A function loaded from a shared library with CasADi's generated-code C ABI (src/codegen_usage.cpp:61-70).
+/// casadi::Function stand-in.  Two kinds, as the reference uses them:
+///  * symbolic: Function(name, {in...}, {out...}, {in names}, {out names}) over SX expressions
+///    (ModelGenerator.cpp:51-53 builds <name>_get_A/_get_B/_get_x_dot_init this way and hands them to
+///    generate_linear_functions); callable numerically and convertible to generated C (codegen::emit_casadi_abi_c);
+///  * external: loaded from a shared library with CasADi's generated-code C ABI (src/codegen_usage.cpp:61-70), see external().
 class Function {
 public:
     Function() = default;
+    Function(const std::string& name, const std::vector<SX>& in, const std::vector<SX>& out, const std::vector<std::string>& in_names = {},
+             const std::vector<std::string>& out_names = {})
+        : m_name(name), m_in(in), m_out(out), m_in_names(in_names), m_out_names(out_names) {}
     std::vector<DM> operator()(const std::vector<DM>& args) const;
     const std::string& name() const { return m_name; }
-    bool is_null() const { return m_fn == nullptr; }
+    bool is_null() const { return m_fn == nullptr && m_out.empty(); }
+    bool is_symbolic() const { return !m_out.empty(); }
+    int n_in() const { return static_cast<int>(m_in.size()); }
+    int n_out() const { return static_cast<int>(m_out.size()); }
+    const std::vector<SX>& sx_in() const { return m_in; }
+    const std::vector<SX>& sx_out() const { return m_out; }
+    const std::vector<std::string>& name_in() const { return m_in_names; }
+    const std::vector<std::string>& name_out() const { return m_out_names; }
 private:
+    std::vector<SX> m_in, m_out;
+    std::vector<std::string> m_in_names, m_out_names;
     friend Function external(const std::string& name, const std::string& lib);
     using eval_t = int (*)(const double**, double**, long long*, double*, int);
     using sp_t = const long long* (*)(long long);

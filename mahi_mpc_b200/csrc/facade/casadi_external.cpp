@@ -21,6 +21,26 @@ Function external(const std::string& name, const std::string& lib) {
 }
 
 std::vector<DM> Function::operator()(const std::vector<DM>& args) const {
+    if (is_symbolic()) {  // numeric evaluation of the expression graph (dense result, structural zeros are zeros)
+        if (args.size() != m_in.size()) throw std::invalid_argument("casadi::Function '" + m_name + "': wrong number of arguments");
+        std::vector<SX> parts;
+        std::vector<double> values;
+        for (size_t a = 0; a < m_in.size(); ++a) {
+            if (static_cast<int>(args[a].nonzeros().size()) != m_in[a].numel())
+                throw std::invalid_argument("casadi::Function '" + m_name + "': argument " + std::to_string(a) + " has the wrong size");
+            for (int j = 0; j < m_in[a].size2(); ++j) for (int i = 0; i < m_in[a].size1(); ++i) parts.push_back(m_in[a](i, j));
+            values.insert(values.end(), args[a].nonzeros().begin(), args[a].nonzeros().end());
+        }
+        const SX vars = SX::vertcat(parts);
+        std::vector<DM> res;
+        for (const SX& o : m_out) {
+            const std::vector<double> v = mahi::mpc::sym::evaluate(o, vars, values);  // column-major like SX
+            DM r(o.size1(), o.size2());
+            for (int j = 0; j < o.size2(); ++j) for (int i = 0; i < o.size1(); ++i) r(i, j) = v[static_cast<size_t>(j) * o.size1() + i];
+            res.push_back(r);
+        }
+        return res;
+    }
     if (!m_fn) throw std::runtime_error("casadi::Function: null function called");
     std::vector<const double*> in;
     for (const DM& a : args) in.push_back(a.nonzeros().data());

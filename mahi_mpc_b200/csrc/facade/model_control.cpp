@@ -18,11 +18,11 @@ void check(int rc, const char* what) {
 }
 
 ModelParameters read_parameters(const std::string& model_name) {
-    std::ifstream file(model_name + ".json");  // ModelControl.cpp:24
+    mahi::util::json j;  // same statements as the reference (ModelControl.cpp:23-26)
+    std::ifstream file(model_name + ".json");
     if (!file) throw std::runtime_error("cannot open " + model_name + ".json");
-    std::stringstream ss;
-    ss << file.rdbuf();
-    return model_parameters_from_json_string(ss.str());
+    file >> j;
+    return j["model"].get<ModelParameters>();
 }
 
 mmpc_options options_from(const casadi::Dict& d) {
@@ -111,7 +111,17 @@ void ModelControl::start_calc() {
                 mahi::util::sleep(mahi::util::microseconds(100));
                 continue;
             }
-            calc_u(local_time, local_state, local_control, std::move(local_traj));
+            try {
+                calc_u(local_time, local_state, local_control, std::move(local_traj));
+            } catch (const std::exception& e) {  // an exception escaping a std::thread body would call std::terminate
+                {
+                    std::lock_guard<std::mutex> lg(m_output_mutex);
+                    m_worker_error = e.what();
+                }
+                std::cerr << "ModelControl: solver thread stopped: " << e.what() << std::endl;
+                m_stop = true;
+                break;
+            }
             calc_times.push_back(timing_clock.get_elapsed_time().as_microseconds() * 1e-3);
         }
         std::cout << "Average calc time: " << mahi::util::mean(calc_times) << " ms" << std::endl;
@@ -145,10 +155,14 @@ void ModelControl::calc_u(mahi::util::Time control_time, const std::vector<doubl
     mmpc_stats st;
     // x_0 pinned to `state`, u_init = `control`, A/B/xdot for linear models evaluated on the device (ModelControl.cpp:125-145)
     check(mmpc_solve(m_solver, state.data(), control.data(), traj.data(), m_V.data(), nullptr, &st, MMPC_MEM_HOST, nullptr), "mmpc_solve");
-    m_info.iterations = st.iterations;
-    m_info.status = st.status;
-    m_info.objective = st.objective;
-    m_info.kkt_error = st.kkt_error;
+    {
+        std::lock_guard<std::mutex> lg(m_output_mutex);  // read by last_solve_info() from other threads
+        m_info.iterations = st.iterations;
+        m_info.status = st.status;
+        m_info.objective = st.objective;
+        m_info.kkt_error = st.kkt_error;
+        m_V_out = m_V;
+    }
     format_outputs(m_V);  // the primal warm start (ModelControl.cpp:161) is kept inside the solver handle
 }
 

@@ -29,6 +29,41 @@ TrajectoryParameters::TrajectoryParameters(std::string name_t_, int num_x_t_, in
     timespan_t = mahi::util::microseconds(step_size_t.as_microseconds() * num_shooting_nodes_t);
 }
 
+void to_json(mahi::util::json& j, const ModelParameters& p) {
+    j = mahi::util::json{{"name", p.name},
+                         {"timespan", p.timespan.as_microseconds()},
+                         {"step_size", p.step_size.as_microseconds()},
+                         {"num_x", p.num_x},
+                         {"num_u", p.num_u},
+                         {"num_shooting_nodes", p.num_shooting_nodes},
+                         {"x_min", p.x_min},
+                         {"u_min", p.u_min},
+                         {"x_max", p.x_max},
+                         {"u_max", p.u_max},
+                         {"dll_filepath", p.dll_filepath},
+                         {"is_linear", p.is_linear}};
+}
+
+void from_json(const mahi::util::json& j, ModelParameters& p) {
+    j.at("name").get_to(p.name);
+    p.timespan = mahi::util::microseconds(j.at("timespan").get<std::int64_t>());
+    p.step_size = mahi::util::microseconds(j.at("step_size").get<std::int64_t>());
+    j.at("num_x").get_to(p.num_x);
+    j.at("num_u").get_to(p.num_u);
+    j.at("num_shooting_nodes").get_to(p.num_shooting_nodes);
+    j.at("x_min").get_to(p.x_min);
+    j.at("u_min").get_to(p.u_min);
+    j.at("x_max").get_to(p.x_max);
+    j.at("u_max").get_to(p.u_max);
+    j.at("dll_filepath").get_to(p.dll_filepath);
+    j.at("is_linear").get_to(p.is_linear);
+    // the reference maps the sentinel to +-inf for x only (ModelParameters.cpp:66-69)
+    for (size_t i = 0; i < p.x_min.size(); ++i) {
+        if (p.x_min[i] == -kNoBound) p.x_min[i] = -std::numeric_limits<double>::infinity();
+        if (p.x_max[i] == kNoBound) p.x_max[i] = std::numeric_limits<double>::infinity();
+    }
+}
+
 static std::string vec_json(const std::vector<double>& v) {
     std::ostringstream os;
     os << "[";

@@ -250,7 +250,7 @@ struct PView {
     }
 };
 
-// One (instance, node) of the whole-NLP callbacks. grid: (ceil(N/128), B), block 128.
+// One (instance, node) of the whole-NLP callbacks. grid: (B, ceil(N/128)) -- the batch on grid.x (no 65535 limit), block 128.
 // f and grad_f are accumulated with atomics (f[b] and the u_{k-1} coupling entries), so the caller
 // zero-fills them first.
 template <class M>
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(128) nlp_eval_kernel(mmpc_problem P, int B, co
                                                        double* __restrict__ grad_f, double* __restrict__ Fx,
                                                        double* __restrict__ Fu, double* __restrict__ Hzz) {
     constexpr int NX = M::NX, NU = M::NU, S = Dim<M>::S, NH = Dim<M>::NH;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y, N = P.N;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x, b = blockIdx.x, N = P.N;
     if (k >= N || b >= B) return;
     const int NV = NX * (N + 1) + NU * N, Mc = N * NX;
     const double* Vb = V + (size_t)b * NV;
@@ -430,7 +430,7 @@ struct Launch {
         cudaError_t e;
         if (f && (e = cudaMemsetAsync(f, 0, sizeof(double) * B, st)) != cudaSuccess) return e;
         if (grad_f && (e = cudaMemsetAsync(grad_f, 0, sizeof(double) * (size_t)B * NV, st)) != cudaSuccess) return e;
-        dim3 grid((P.N + 127) / 128, B);
+        dim3 grid(B, (P.N + 127) / 128);
         nlp_eval_kernel<M><<<grid, 128, 0, st>>>(P, B, V, p, lam, lam_f, f, g, grad_f, Fx, Fu, Hzz);
         if (launches) ++*launches;
         return cudaGetLastError();
@@ -503,5 +503,7 @@ struct Launch {
     MMPC_DEFINE_SOLVE_T1(MODEL) MMPC_DEFINE_SOLVE_T2(MODEL) MMPC_DEFINE_SOLVE_T3(MODEL) MMPC_DEFINE_MODEL_CORE(MODEL)
 // Additionally exports the generic entry point a stand-alone generated model library is dlopen'ed by
 // (the role `nlpsol("nlpsol","ipopt",dll,...)` plays at ModelControl.cpp:61-62).
+// Generated libraries are compiled with -fvisibility=hidden: only this entry is exported, so a user model whose
+// identifier equals a built-in's cannot be interposed by the copies inside libmahi_mpc_b200.so (global scope).
 #define MMPC_EXPORT_MODEL_ENTRY(MODEL) \
-    extern "C" const mmpc_model_vtable* mmpc_model_vtable_get(void) { return mmpc_vtable_##MODEL(); }
+    extern "C" __attribute__((visibility("default"))) const mmpc_model_vtable* mmpc_model_vtable_get(void) { return mmpc_vtable_##MODEL(); }

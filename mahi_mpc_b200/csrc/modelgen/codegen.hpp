@@ -8,6 +8,7 @@
 //                                          (src/codegen_usage.cpp:61-70,118-132)
 #pragma once
 #include <string>
+#include <vector>
 
 #include "../expr/sx.hpp"
 
@@ -25,6 +26,17 @@ std::string emit_cuda_model(const ModelExpr& m);
 
 /// Translation unit that instantiates every kernel for the model and exports its vtable.
 std::string emit_cuda_unit(const std::string& name, const std::string& model_header);
+
+/// A named symbolic function (what casadi::Function(name, {in...}, {out...}, {in names}, {out names}) holds).
+struct SymFunction {
+    std::string name;
+    std::vector<sym::SX> in, out;
+    std::vector<std::string> in_names, out_names;
+};
+
+/// C source exporting every function of `fns` with CasADi's generated-code ABI (what casadi::CodeGenerator emits,
+/// ModelGenerator.cpp:241-246): dense inputs, outputs as the structural non-zeros in CCS order.
+std::string emit_casadi_abi_c(const std::string& banner, const std::vector<SymFunction>& fns);
 
 /// C source of <name>_linear_functions (CasADi ABI).
 std::string emit_linear_functions_c(const ModelExpr& m);

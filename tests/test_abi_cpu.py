@@ -68,6 +68,21 @@ def test_model_load_json_reference_schema(api, tmp_path):
                    "u_max": [1e31] * 2, "dll_filepath": "nonlinear_double_pendulum.so", "is_linear": False}}
     path = tmp_path / "nonlinear_double_pendulum.json"
     path.write_text(json.dumps(j))
+    # the library the artefact names is absent (or is the reference's CasADi CPU library): an error, never a silent switch to
+    # the built-in L = m = 1 dynamics
+    with pytest.raises(api.MmpcError) as e:
+        api.Model(json_name=str(tmp_path / "nonlinear_double_pendulum"))
+    assert e.value.code == -5 and "nonlinear_double_pendulum.so" in str(e.value)
+    (tmp_path / "cpu_only.c").write_text("int nlp_f(void) { return 0; }\n")
+    import subprocess
+    subprocess.run(["gcc", "-shared", "-fPIC", str(tmp_path / "cpu_only.c"), "-o", str(tmp_path / "cpu_only.so")], check=True)
+    j["model"]["dll_filepath"] = str(tmp_path / "cpu_only.so")
+    path.write_text(json.dumps(j))
+    with pytest.raises(api.MmpcError) as e:
+        api.Model(json_name=str(tmp_path / "nonlinear_double_pendulum"))
+    assert e.value.code == -5 and "not a mahi-mpc-b200 CUDA model library" in str(e.value)
+    j["model"]["dll_filepath"] = "builtin:double_pendulum"  # explicit request for a built-in kernel set
+    path.write_text(json.dumps(j))
     m = api.Model(json_name=str(tmp_path / "nonlinear_double_pendulum"))
     assert (m.nx, m.nu, m.N, m.h) == (4, 2, 25, 0.002)
     with pytest.raises(api.MmpcError) as e:

@@ -273,15 +273,18 @@ def test_solve_headline_config_vs_oracle(api, coracle):
     the reference's tol = 1e-5 (ModelControl.cpp:54)."""
     N, B = 50, 4096
     P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B)
-    Vo, lamo, sto, bad = coracle.solve_batch("double_pendulum", N, P.h, False, x0, p, tol=1e-10)
+    Vt, _, stt, bad = coracle.solve_batch("double_pendulum", N, P.h, False, x0, p, tol=1e-10)
     assert bad == 0
     m = api.Model("double_pendulum", N=N)
     for tol in (1e-10, 1e-5):
+        # north_star: "... at the same tolerance settings": the oracle stops by the same rule at the same tol
+        Vo, lamo, sto, bad = coracle.solve_batch("double_pendulum", N, P.h, False, x0, p, tol=tol)
+        assert bad == 0
         s = api.Solver(m, B, tol=tol, warm_start=0)
         s.set_weights(Q, R, Rm)
         V, lam, st = s.solve(x0, up, traj)
         assert (st["status"] == 0).all()
-        assert np.abs(V - Vo).max() < U_ATOL
+        assert np.abs(V - Vo).max() < U_ATOL and np.abs(V - Vt).max() < U_ATOL  # ... and inside the ball of the tight solution
         assert (np.abs(st["objective"] - sto["f"]) <= OBJ_RTOL * np.abs(sto["f"])).all()
         if tol == 1e-10:
             assert np.abs(V - Vo).max() < 1e-8 and rel(lam, lamo) < 1e-7
