@@ -391,6 +391,7 @@ __device__ __forceinline__ void chol_solve(const double* L, double* b) {
 #include "mmpc_solve_t1.cuh"
 #include "mmpc_solve_t2.cuh"
 #include "mmpc_solve_t3.cuh"
+#include "mmpc_solve_t4.cuh"
 namespace mmpc {
 
 // ---------------------------------------------------------------------------------------------
@@ -455,6 +456,9 @@ struct Launch {
     static cudaError_t solve_t3(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         return LaunchT3<M>::run(P, W, io, st);
     }
+    static cudaError_t solve_t4(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
+        return LaunchT4<M>::run(P, W, io, st);
+    }
 };
 
 }  // namespace mmpc
@@ -473,11 +477,16 @@ struct Launch {
     extern "C" cudaError_t mmpc_solve_t3_##MODEL(const mmpc_problem* P, const mmpc_workspace* W, const mmpc_solve_io* io, cudaStream_t st) { \
         return mmpc::Launch<mmpc_model_##MODEL>::solve_t3(*P, *W, *io, st);                                             \
     }
+#define MMPC_DEFINE_SOLVE_T4(MODEL)                                                                                    \
+    extern "C" cudaError_t mmpc_solve_t4_##MODEL(const mmpc_problem* P, const mmpc_workspace* W, const mmpc_solve_io* io, cudaStream_t st) { \
+        return mmpc::Launch<mmpc_model_##MODEL>::solve_t4(*P, *W, *io, st);                                             \
+    }
 // ... and this one defines the evaluators, the solve dispatcher and `mmpc_vtable_<MODEL>()`:
 #define MMPC_DEFINE_MODEL_CORE(MODEL)                                                                                   \
     extern "C" cudaError_t mmpc_solve_t1_##MODEL(const mmpc_problem*, const mmpc_workspace*, const mmpc_solve_io*, cudaStream_t); \
     extern "C" cudaError_t mmpc_solve_t2_##MODEL(const mmpc_problem*, const mmpc_workspace*, const mmpc_solve_io*, cudaStream_t); \
     extern "C" cudaError_t mmpc_solve_t3_##MODEL(const mmpc_problem*, const mmpc_workspace*, const mmpc_solve_io*, cudaStream_t); \
+    extern "C" cudaError_t mmpc_solve_t4_##MODEL(const mmpc_problem*, const mmpc_workspace*, const mmpc_solve_io*, cudaStream_t); \
     static cudaError_t mmpc_solve_dispatch_##MODEL(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io,  \
                                                    cudaStream_t st, int* launches) {                                    \
         if (P.integrator == MMPC_RK4 && P.is_linear) return cudaErrorNotSupported;                                      \
@@ -487,6 +496,7 @@ struct Launch {
         if (launches) ++*launches;                                                                                      \
         if (W.variant == 2) return mmpc_solve_t2_##MODEL(&P, &W, &io, st);                                              \
         if (W.variant == 3) return mmpc_solve_t3_##MODEL(&P, &W, &io, st);                                              \
+        if (W.variant == 4) return mmpc_solve_t4_##MODEL(&P, &W, &io, st);                                              \
         return mmpc_solve_t1_##MODEL(&P, &W, &io, st);                                                                  \
     }                                                                                                                   \
     extern "C" const mmpc_model_vtable* mmpc_vtable_##MODEL(void) {                                                      \
@@ -500,7 +510,7 @@ struct Launch {
     }
 // everything in one unit (what ModelGenerator::generate_c_code emits for a user model)
 #define MMPC_DEFINE_MODEL(MODEL) \
-    MMPC_DEFINE_SOLVE_T1(MODEL) MMPC_DEFINE_SOLVE_T2(MODEL) MMPC_DEFINE_SOLVE_T3(MODEL) MMPC_DEFINE_MODEL_CORE(MODEL)
+    MMPC_DEFINE_SOLVE_T1(MODEL) MMPC_DEFINE_SOLVE_T2(MODEL) MMPC_DEFINE_SOLVE_T3(MODEL) MMPC_DEFINE_SOLVE_T4(MODEL) MMPC_DEFINE_MODEL_CORE(MODEL)
 // Additionally exports the generic entry point a stand-alone generated model library is dlopen'ed by
 // (the role `nlpsol("nlpsol","ipopt",dll,...)` plays at ModelControl.cpp:61-62).
 // Generated libraries are compiled with -fvisibility=hidden: only this entry is exported, so a user model whose

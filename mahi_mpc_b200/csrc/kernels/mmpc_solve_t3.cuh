@@ -615,6 +615,7 @@ __device__ __noinline__ void t3_residuals(const T3Ctx<M, C::I, C::MODE>& cin, do
             red[(7 * C::CB + wj) * I + wi] = n.cmin;  red[(8 * C::CB + wj) * I + wi] = n.barrier;
         }
     }
+    __syncwarp();  // node groups of one warp may differ in trip count (tile widths below 32): arrive at the aligned CTA barrier together
     __syncthreads();
     T3NormsBD o;
     o.dual_inf = o.prim_inf = o.theta = o.fval = o.lam_l1 = o.z_l1 = o.cmax = o.barrier = 0.0;
@@ -893,6 +894,7 @@ __device__ __noinline__ void t3_trial(const T3Ctx<M, C::I, C::MODE>& cin, double
         red[(1 * C::CB + wj) * I + wi] = a2;
         if constexpr (C::BD) red[(2 * C::CB + wj) * I + wi] = bd.bar1;
     }
+    __syncwarp();  // as in t3_residuals
     __syncthreads();
     f1 = 0.0; th1 = 0.0; bar1 = 0.0;
     if (tid < I) MMPC_UNROLL for (int s = 0; s < C::CB; ++s) {

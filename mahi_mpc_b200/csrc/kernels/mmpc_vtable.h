@@ -6,7 +6,7 @@
 
 #define MMPC_MAXNX 16
 #define MMPC_MAXNU 8
-#define MMPC_VTABLE_VERSION 5
+#define MMPC_VTABLE_VERSION 6
 
 struct mmpc_stats;  // public struct (include/mahi_mpc_b200.h)
 
@@ -55,8 +55,18 @@ struct mmpc_workspace {
     double *KG2;    // B * N * (nu*(nx+nu) + nu)               feedback gains
     double *PG2;    // B * N * (nx*(nx+nu+1))                  rows of the value function needed for lam
     double *LIN2;   // B * (nx*nx + nx*nu + nx)
-    int variant;    // kernel variant the persistent state belongs to (1 = T1, 2 = T2)
+    int variant;    // kernel variant the persistent state belongs to (1 = T1, 2 = T2, 3 = T3, 4 = T4)
 };
+
+// Tile width (instances per CTA) of kernel variant T4 for a handle of `batch` instances: the narrowest of 4 / 14 / 28 that still
+// covers the batch with one CTA per SM of a 148-SM B200 (mmpc_solve_t4.cuh).  `forced` = kernel_variant >> 8 (1, 2, 3 pick one).
+// The ABI layer cuts host-buffer sub-batches on multiples of it.
+static inline int mmpc_t4_tile_width(int batch, int forced) {
+    if (forced == 1) return 4;
+    if (forced == 2) return 14;
+    if (forced == 3) return 28;
+    return batch <= 148 * 4 ? 4 : (batch <= 148 * 14 ? 14 : 28);
+}
 
 struct mmpc_solve_io {
     const double *state, *control, *traj;  // AoS device pointers (B*nx, B*nu, B*N*nx)

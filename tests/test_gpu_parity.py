@@ -177,8 +177,12 @@ def test_solve_vs_golden(api, golden):
         assert rel(lam[0], case["lam_g"]) < 1e-6
 
 
-# 3 + 256*2 forces T3's 32-instance tile configuration (chosen automatically only for batches beyond 1184) on ragged small batches
-@pytest.mark.parametrize("variant", [1, 2, 3, 3 + 256 * 2])
+# 3 + 256*2 forces T3's 32-instance tile configuration (chosen automatically only for batches beyond 1184) on ragged small batches;
+# 4 + 256*k forces T4's tile width 4 / 14 / 28 (chosen from the batch size otherwise: 4 here)
+SOLVE_VARIANTS = [1, 2, 3, 3 + 256 * 2, 4 + 256 * 1, 4 + 256 * 2, 4 + 256 * 3]
+
+
+@pytest.mark.parametrize("variant", SOLVE_VARIANTS)
 @pytest.mark.parametrize("N,B", [(1, 3), (10, 7), (25, 33), (50, 64), (100, 8), (200, 4)])
 def test_solve_vs_oracle(api, coracle, N, B, variant):
     P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B)
@@ -293,7 +297,7 @@ def test_solve_headline_config_vs_oracle(api, coracle):
         s.close()
 
 
-@pytest.mark.parametrize("variant", [1, 3, 3 + 256 * 2])
+@pytest.mark.parametrize("variant", [1, 3, 3 + 256 * 2, 4 + 256 * 1, 4 + 256 * 3])
 @pytest.mark.parametrize("N,B", [(25, 40), (50, 64)])
 def test_linearised_solve_vs_oracle(api, coracle, N, B, variant):
     """is_linear models (ModelGenerator.cpp:38-58) -- the kernel linearises f at (state, control) itself
@@ -550,7 +554,7 @@ def test_closed_loop_batch_vs_oracle(api, coracle, plant):
     assert (it[:, 1:] <= it[:, :1]).all() and (it >= 0).all()             # warm starts never need more than the cold solve
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 3 + 256 * 2])
+@pytest.mark.parametrize("variant", SOLVE_VARIANTS)
 def test_failed_instance_does_not_poison_the_batch(api, coracle, variant):
     """SURVEY section 5 (failure detection): a non-finite input makes THAT instance report MMPC_SOLVE_NUMERICAL; its
     neighbours (same warp / same CTA tile) still converge to the oracle's solution."""
