@@ -20,8 +20,13 @@
 // Euler / linearised shooting, no finite bounds (those stay on T3 / T1).  Replaces IPOPT+MUMPS at ModelControl.cpp:159.
 #pragma once
 #include <cstdint>
-#ifdef MMPC_T4_DEBUG
+#if defined(MMPC_T4_DEBUG) || defined(MMPC_T4_PROFILE)
 #include <cstdio>
+#endif
+#ifdef MMPC_T4_PROFILE
+#define T4_CLK() clock64()
+#else
+#define T4_CLK() 0LL
 #endif
 
 namespace mmpc {
@@ -36,6 +41,15 @@ __device__ __forceinline__ void t4_mbar_inval(unsigned long long* bar) {
 }
 __device__ __forceinline__ void t4_mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t4_smem_u32(bar)) : "memory");
+}
+// arrival that orders nothing: for "I have finished READING this slot" (the reads fed arithmetic that has completed) -- a
+// releasing arrival would first wait for the thread's outstanding global stores (gains, value-function rows)
+__device__ __forceinline__ void t4_mbar_arrive_relaxed(unsigned long long* bar) {
+#ifdef MMPC_T4_RELEASE_ARRIVE
+    t4_mbar_arrive(bar);
+#else
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(t4_smem_u32(bar)) : "memory");
+#endif
 }
 __device__ __forceinline__ void t4_mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(t4_smem_u32(bar)), "r"(bytes) : "memory");
@@ -158,8 +172,10 @@ struct T4 {
                          XS_RAW = XS_KX + NX * NU;
     // stride between instances: an odd number of 16-byte units, so that the instances of a warp hit different bank groups
     static constexpr int XSI = ((XS_RAW + 1) / 2 * 2) + ((((XS_RAW + 1) / 2) % 2 == 0) ? 2 : 0);
-    static constexpr int SM_REC = 0, SM_RED = NSLOT * SLOT, SM_INST = SM_RED + REDBUF, SM_XS = SM_INST + 6 * I, SM_BAR = SM_XS + SWARPS * IPW * XSI,
-                         SM_END = SM_BAR + 2 * NSLOT;
+    // per-instance constants the evaluators read from shared memory: Q | R | Rm | u_init | regularisation delta
+    static constexpr int CS_Q = 0, CS_R = NX, CS_RM = NX + NU, CS_U0 = NX + 2 * NU, CS_DELTA = NX + 3 * NU, NCST = CS_DELTA + 1;
+    static constexpr int SM_REC = 0, SM_RED = NSLOT * SLOT, SM_INST = SM_RED + REDBUF, SM_XS = SM_INST + 6 * I, SM_CST = SM_XS + SWARPS * IPW * XSI,
+                         SM_BAR = SM_CST + NCST * I, SM_END = SM_BAR + 2 * NSLOT;
     static constexpr size_t SMEM_BYTES = sizeof(double) * SM_END;
     static constexpr int LIN = NX * NX + NX * NU + NX;
 };
@@ -177,13 +193,11 @@ __device__ __forceinline__ double t4_pick(const double* v, int a) {
     return r;
 }
 
-struct T4Acc {  // KKT residual pieces accumulated by a worker thread over its nodes
-    double dual, prim, theta, fval, lam1;
-};
-
 // ---- worker: node k of instance i -> ring slot (recursion inputs) + global record (roll-out inputs) + residual pieces ----
+// Per-instance constants (weights, u_init, regularisation) come from shared memory and the residual pieces are accumulated in
+// shared memory: the evaluator's registers hold the model evaluation and little else (128 per thread at 512 threads per CTA).
 template <class M, class C>
-__device__ __forceinline__ void t4_eval_node(const T3Ctx<M, C::I, 0>& c, int k, double delta, double* slot_i, double* recg_i, T4Acc& acc,
+__device__ __forceinline__ void t4_eval_node(const T3Ctx<M, C::I, 0>& c, int k, const double* cst_i, double* slot_i, double* recg_i, double* red_i,
                                              unsigned long long* empty_bar, int empty_parity) {
     constexpr int NX = M::NX, NU = M::NU, S = C::S, NH = C::NH, I = C::I;
     const int N = c.N;
@@ -193,7 +207,7 @@ __device__ __forceinline__ void t4_eval_node(const T3Ctx<M, C::I, 0>& c, int k, 
         x[a] = z[a * I];
         r[a] = c.traj[(size_t)k * NX + a];
         lam[a] = c.LAM[((size_t)k * NX + a) * I];
-        wq[a] = 2.0 * c.Q[a];
+        wq[a] = 2.0 * cst_i[(C::CS_Q + a) * I];
     }
     MMPC_UNROLL for (int a = 0; a < NU; ++a) u[a] = z[(NX + a) * I];
     double F[NX], Fx[NX * NX], Fu[NX * NU], H[NH];
@@ -206,20 +220,20 @@ __device__ __forceinline__ void t4_eval_node(const T3Ctx<M, C::I, 0>& c, int k, 
         lam_prev[a] = k ? c.LAM[((size_t)(k - 1) * NX + a) * I] : 0.0;
     }
     MMPC_UNROLL for (int a = 0; a < NU; ++a) {
-        v[a] = k ? z[(NX + a - S) * I] : c.uinit[a];
+        v[a] = k ? z[(NX + a - S) * I] : cst_i[(C::CS_U0 + a) * I];
         u_next[a] = (k < N - 1) ? z[(S + NX + a) * I] : 0.0;
     }
     if (empty_parity >= 0) t4_mbar_wait(empty_bar, (unsigned)empty_parity, 1, k);  // the recursion has released the slot's previous node
 #define T4_REC(f) slot_i[(f) * I]
 #define T4_FG(f, val) recg_i[(f) * I] = (val)
-    double qe[NX], dual = 0.0;
+    double qe[NX], dual = 0.0, prim = 0.0, theta = 0.0, fval = 0.0, lam1 = 0.0;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         const double e = F[a] - r[a], cr = F[a] - xn[a];
         qe[a] = wq[a] * e;
-        acc.fval = fma(c.Q[a] * e, e, acc.fval);
-        acc.prim = fmax(acc.prim, fabs(cr));
-        acc.theta += fabs(cr);
-        acc.lam1 += fabs(lam[a]);
+        fval = fma(0.5 * wq[a] * e, e, fval);
+        prim = fmax(prim, fabs(cr));
+        theta += fabs(cr);
+        lam1 += fabs(lam[a]);
         T4_REC(C::RB_C + a) = cr;
         T4_FG(C::FG_C + a, cr);
         if (k == N - 1) dual = fmax(dual, fabs(lam[a]));  // stationarity w.r.t. x_N is -lam_{N-1}
@@ -242,22 +256,31 @@ __device__ __forceinline__ void t4_eval_node(const T3Ctx<M, C::I, 0>& c, int k, 
         T4_FG(C::FG_Q + a, g);
         if (k) dual = fmax(dual, fabs(g + l - lam_prev[a]));
     }
+    double RRm2[NU];  // 2 (R + Rm): diagonal of the control block
     MMPC_UNROLL for (int a = 0; a < NU; ++a) {
         double g = 0.0, l = 0.0;
         MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T4_FUNZ(q, a)) {
             g = fma(Fu[q * NU + a], qe[q], g);
             l = fma(Fu[q * NU + a], lam[q], l);
         }
-        const double du = u[a] - v[a], dRu = 2.0 * c.R[a] * du;
-        const double qu = g + dRu + 2.0 * c.Rm[a] * u[a];
-        const double dRn = (k < N - 1) ? 2.0 * c.R[a] * (u_next[a] - u[a]) : 0.0;
-        acc.fval = fma(c.R[a] * du, du, acc.fval);
-        acc.fval = fma(c.Rm[a] * u[a], u[a], acc.fval);
+        const double Ra = cst_i[(C::CS_R + a) * I], Rma = cst_i[(C::CS_RM + a) * I];
+        RRm2[a] = 2.0 * (Ra + Rma);
+        const double du = u[a] - v[a], dRu = 2.0 * Ra * du;
+        const double qu = g + dRu + 2.0 * Rma * u[a];
+        const double dRn = (k < N - 1) ? 2.0 * Ra * (u_next[a] - u[a]) : 0.0;
+        fval = fma(Ra * du, du, fval);
+        fval = fma(Rma * u[a], u[a], fval);
         dual = fmax(dual, fabs(qu + l - dRn));
         T4_REC(C::RB_Q + NX + a) = -dRu;  T4_FG(C::FG_Q + NX + a, -dRu);
         T4_REC(C::RB_Q + S + a) = qu;     T4_FG(C::FG_Q + S + a, qu);
     }
-    acc.dual = fmax(acc.dual, dual);
+    // residual pieces of the iterate: running max / sums of this worker thread over its nodes, kept in shared memory
+    red_i[0 * C::CB * I] = fmax(red_i[0 * C::CB * I], dual);
+    red_i[1 * C::CB * I] = fmax(red_i[1 * C::CB * I], prim);
+    red_i[2 * C::CB * I] += theta;
+    red_i[3 * C::CB * I] += fval;
+    red_i[4 * C::CB * I] += lam1;
+    const double delta = cst_i[C::CS_DELTA * I];
     MMPC_UNROLL for (int p = 0; p < S; ++p) MMPC_UNROLL for (int d = p; d < S; ++d) {
         double t = H[tri(p, d, S)];
         MMPC_UNROLL for (int q = 0; q < NX; ++q) {
@@ -268,7 +291,7 @@ __device__ __forceinline__ void t4_eval_node(const T3Ctx<M, C::I, 0>& c, int k, 
                 t = fma(wq[q] * fa, fd, t);
             }
         }
-        if (p == d) t += delta + (p >= NX ? 2.0 * (c.R[p - NX] + c.Rm[p - NX]) : 0.0);
+        if (p == d) t += delta + (p >= NX ? RRm2[p - NX] : 0.0);
         T4_REC(C::RB_H + tri(p, d, S)) = t;
     }
 #undef T4_REC
@@ -291,11 +314,26 @@ struct T4Lane {
     int pxoff[C::NX];  // (PG_XX + packed index of Pxx[a][q]) * I
 };
 
+// One stage.  Written as "load everything the phase needs, then compute": with the loads of a phase issued back to back their
+// ~30-cycle shared-memory latencies overlap (the first version interleaved every LDS with the DFMA that needed it: 2.2 k cycles
+// per stage on the GPU).
 template <class M, class C>
 __device__ __forceinline__ bool t4_riccati_stage(T4Riccati<M>& V, const T4Lane<C>& ln, const double* rp, double* xs, const double* R, double* recg, bool wr) {
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
     const int a = ln.a;
     const double* rpa = rp + a * I;
+    // ---- loads of the whole stage from the ring record: uniform fields (every lane of the instance reads the same ones) and
+    // the lane's own row / column ----
+    double Fx[NX * NX], Fu[NX * NU], cres[NX], Fxc[NX], Hx[NX], Hu[NU], Huu[NU * (NU + 1) / 2], qu[NU], qvv[NU];
+    MMPC_UNROLL for (int q = 0; q < NX * NX; ++q) Fx[q] = T4_FXNZ(q / NX, q % NX) ? rp[(C::RB_FX + q) * I] : 0.0;
+    MMPC_UNROLL for (int q = 0; q < NX * NU; ++q) Fu[q] = T4_FUNZ(q / NU, q % NU) ? rp[(C::RB_FU + q) * I] : 0.0;
+    MMPC_UNROLL for (int q = 0; q < NX; ++q) cres[q] = rp[(C::RB_C + q) * I];
+    MMPC_UNROLL for (int q = 0; q < NX; ++q) Fxc[q] = rpa[(C::RB_FX + q * NX) * I];  // column a of Fx
+    MMPC_UNROLL for (int b = 0; b < NX; ++b) Hx[b] = rp[ln.hoff[b]];
+    MMPC_UNROLL for (int b = 0; b < NU; ++b) Hu[b] = rp[ln.hoff[NX + b]];
+    MMPC_UNROLL for (int p = 0; p < NU; ++p) MMPC_UNROLL for (int d = p; d < NU; ++d) Huu[tri(p, d, NU)] = rp[(C::RB_H + tri(NX + p, NX + d, S)) * I];
+    const double qxa = rpa[C::RB_Q * I];
+    MMPC_UNROLL for (int p = 0; p < NU; ++p) { qvv[p] = rp[(C::RB_Q + NX + p) * I]; qu[p] = rp[(C::RB_Q + S + p) * I]; }
     // ---- value function of stage k+1 -> global record (the roll-out needs it for lam_k); lane a writes its row ----
     if (wr) {
         double* pg = recg + (size_t)C::RF_P * I;
@@ -303,13 +341,8 @@ __device__ __forceinline__ bool t4_riccati_stage(T4Riccati<M>& V, const T4Lane<C
         MMPC_UNROLL for (int b = 0; b < NU; ++b) pg[(C::PG_XV + a * NU + b) * I] = V.Pxv[b];
         pg[(C::PG_X + a) * I] = V.px;
     }
-    // ---- step 1: row a of P Fx, P Fu + Pxv and y = p + P c (uniform reads: every lane of the instance reads the same record fields) ----
-    double Fu[NX * NU], cres[NX];
-    MMPC_UNROLL for (int q = 0; q < NX * NU; ++q) Fu[q] = T4_FUNZ(q / NU, q % NU) ? rp[(C::RB_FU + q) * I] : 0.0;
-    MMPC_UNROLL for (int q = 0; q < NX; ++q) cres[q] = rp[(C::RB_C + q) * I];
+    // ---- step 1: row a of P Fx, P Fu + Pxv and y = p + P c ----
     {
-        double Fx[NX * NX];
-        MMPC_UNROLL for (int q = 0; q < NX * NX; ++q) Fx[q] = T4_FXNZ(q / NX, q % NX) ? rp[(C::RB_FX + q) * I] : 0.0;
         double y = V.px;
         MMPC_UNROLL for (int q = 0; q < NX; ++q) y = fma(V.Pxx[q], cres[q], y);
         xs[C::XS_Y + a] = y;
@@ -327,44 +360,39 @@ __device__ __forceinline__ bool t4_riccati_stage(T4Riccati<M>& V, const T4Lane<C
     }
     __syncwarp();
     // ---- step 2: row a of the stage matrices G = H + Z' P Z, the (replicated) control block and the gains ----
-    double Fxc[NX];  // column a of Fx
-    MMPC_UNROLL for (int q = 0; q < NX; ++q) Fxc[q] = rpa[(C::RB_FX + q * NX) * I];
-    double Gxx[NX], Gxu[NU], gx;
-    {
-        double Y[NX];
-        MMPC_UNROLL for (int q = 0; q < NX; ++q) Y[q] = xs[C::XS_Y + q];
-        gx = rpa[C::RB_Q * I];
-        MMPC_UNROLL for (int q = 0; q < NX; ++q) gx = fma(Fxc[q], Y[q], gx);
-        MMPC_UNROLL for (int b = 0; b < NX; ++b) {
-            double t = rp[ln.hoff[b]];
-            MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(Fxc[q], xs[C::XS_PA + q * NX + b], t);
-            Gxx[b] = t;
-        }
-    }
-    double PB[NX * NU], PV[NX * NU];
+    double PA[NX * NX], PB[NX * NU], PV[NX * NU], Y[NX];
+    MMPC_UNROLL for (int q = 0; q < NX * NX; ++q) PA[q] = xs[C::XS_PA + q];
     MMPC_UNROLL for (int q = 0; q < NX * NU; ++q) { PB[q] = xs[C::XS_PB + q]; PV[q] = xs[C::XS_PV + q]; }
+    MMPC_UNROLL for (int q = 0; q < NX; ++q) Y[q] = xs[C::XS_Y + q];
+    double Gxx[NX], Gxu[NU], gx = qxa;
+    MMPC_UNROLL for (int q = 0; q < NX; ++q) gx = fma(Fxc[q], Y[q], gx);
+    MMPC_UNROLL for (int b = 0; b < NX; ++b) {
+        double t = Hx[b];
+        MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(Fxc[q], PA[q * NX + b], t);
+        Gxx[b] = t;
+    }
     MMPC_UNROLL for (int b = 0; b < NU; ++b) {
-        double t = rp[ln.hoff[NX + b]];
+        double t = Hu[b];
         MMPC_UNROLL for (int q = 0; q < NX; ++q) t = fma(Fxc[q], PB[q * NU + b], t);
         Gxu[b] = t;
     }
     double Guu[NU * NU], gu[NU];
     MMPC_UNROLL for (int p = 0; p < NU; ++p) {
         MMPC_UNROLL for (int d = p; d < NU; ++d) {
-            double t = rp[(C::RB_H + tri(NX + p, NX + d, S)) * I] + 0.5 * (V.Pvv[p * NU + d] + V.Pvv[d * NU + p]);
+            double t = Huu[tri(p, d, NU)] + 0.5 * (V.Pvv[p * NU + d] + V.Pvv[d * NU + p]), t2 = 0.0;  // two chains
             MMPC_UNROLL for (int q = 0; q < NX; ++q) {
                 if (T4_FUNZ(q, p)) t = fma(Fu[q * NU + p], PB[q * NU + d], t);
-                if (T4_FUNZ(q, d)) t = fma(PV[q * NU + p], Fu[q * NU + d], t);
+                if (T4_FUNZ(q, d)) t2 = fma(PV[q * NU + p], Fu[q * NU + d], t2);
             }
-            Guu[p * NU + d] = t;
-            Guu[d * NU + p] = t;
+            Guu[p * NU + d] = t + t2;
+            Guu[d * NU + p] = t + t2;
         }
-        double t = rp[(C::RB_Q + S + p) * I] + V.pv[p];
+        double t = qu[p] + V.pv[p], t2 = 0.0;
         MMPC_UNROLL for (int q = 0; q < NX; ++q) {
             t = fma(PV[q * NU + p], cres[q], t);
-            if (T4_FUNZ(q, p)) t = fma(Fu[q * NU + p], xs[C::XS_Y + q], t);
+            if (T4_FUNZ(q, p)) t2 = fma(Fu[q * NU + p], Y[q], t2);
         }
-        gu[p] = t;
+        gu[p] = t + t2;
     }
     bool ok;
     double Kxc[NU], Kv[NU * NU], k0[NU];  // column a of Kx; Kv and k0 replicated
@@ -393,7 +421,11 @@ __device__ __forceinline__ bool t4_riccati_stage(T4Riccati<M>& V, const T4Lane<C
         chol_solve<NU>(Guu, k0);
     }
     MMPC_UNROLL for (int l = 0; l < NU; ++l) xs[C::XS_KX + a * NU + l] = Kxc[l];
-    if (wr) {
+    __syncwarp();
+    // ---- step 3: row a of the value function of stage k ----
+    double KX[NX * NU];
+    MMPC_UNROLL for (int q = 0; q < NX * NU; ++q) KX[q] = xs[C::XS_KX + q];
+    if (wr) {  // gains -> global record (after the exchange: off the stage's dependent chain)
         double* kg = recg + (size_t)C::RF_K * I;
         MMPC_UNROLL for (int l = 0; l < NU; ++l) kg[(C::KG_KX + l * NX + a) * I] = Kxc[l];
         if (a == 0) {
@@ -401,13 +433,9 @@ __device__ __forceinline__ bool t4_riccati_stage(T4Riccati<M>& V, const T4Lane<C
             MMPC_UNROLL for (int q = 0; q < NU; ++q) kg[(C::KG_K0 + q) * I] = k0[q];
         }
     }
-    double qvv[NU];
-    MMPC_UNROLL for (int p = 0; p < NU; ++p) qvv[p] = rp[(C::RB_Q + NX + p) * I];
-    __syncwarp();
-    // ---- step 3: row a of the value function of stage k ----
     MMPC_UNROLL for (int b = 0; b < NX; ++b) {
         double t = Gxx[b];
-        MMPC_UNROLL for (int l = 0; l < NU; ++l) t = fma(Gxu[l], xs[C::XS_KX + b * NU + l], t);
+        MMPC_UNROLL for (int l = 0; l < NU; ++l) t = fma(Gxu[l], KX[b * NU + l], t);
         V.Pxx[b] = t;
     }
     MMPC_UNROLL for (int b = 0; b < NU; ++b) {
@@ -448,70 +476,91 @@ __device__ __forceinline__ void t4_sweep_entry() {
 }
 
 // ---- backward sweep: node evaluation (workers) -> ring -> Riccati recursion (serial warps) ----------------------------------
-// returns (serial lanes) whether every G_uu was positive definite; residual norms of the iterate on the master lanes
+// The two roles are separate non-inlined functions: ptxas allocates registers and schedules per function, and the recursion's
+// short dependent chains were scheduled for minimum register use while they shared a function with the evaluator.
 template <class M, class C>
-__device__ T4_SWEEP bool t4_backward(const T3Ctx<M, C::I, 0>& cin, double* smem, int tid, double delta_self, bool master, int inst, T3Norms& nrm_out,
-                                         double* rec_tile, int& ring_phase) {
-    constexpr int NX = M::NX, NU = M::NU, I = C::I, S = C::S;
+__device__ __noinline__ void t4_bwd_worker(const T3Ctx<M, C::I, 0>& cin, double* smem, int tid, double* rec_tile, int base, int R) {
+    constexpr int I = C::I;
     const T3Ctx<M, C::I, 0> c = cin;
     const int N = c.N;
-    double* dl = smem + C::SM_INST;
-    double* red = smem + C::SM_RED;
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + C::SM_BAR);
     unsigned long long* empty = full + C::NSLOT;
-    if (master) dl[inst] = delta_self;
+    const int w = C::widx(tid), wi = w % I, wj = w / I;
+    double* red_i = smem + C::SM_RED + wj * I + wi;  // row n of this thread's residual pieces: red_i[n * CB * I]
+    MMPC_UNROLL for (int n = 0; n < C::NRED; ++n) red_i[n * C::CB * I] = 0.0;
+    const double* cst_i = smem + C::SM_CST + wi;
+    const long long tw0 = T4_CLK();
+    for (int r = 0; r < R; ++r) {
+        const int u = wj + r * C::CB, ph = base + r;  // u-th node of the sweep: k = N-1-u
+        if (u < N) {
+            const int k = N - 1 - u;
+            if (u + C::CB < N) t3_prefetch_node<M, C>(c, k - C::CB);
+            t4_eval_node<M, C>(c, k, cst_i, smem + C::SM_REC + (size_t)wj * C::SLOT + wi, rec_tile + (size_t)k * C::RF * I + wi, red_i, &empty[wj],
+                               ph > 0 ? ((ph - 1) & 1) : -1);
+        } else if (ph > 0) {
+            t4_mbar_wait(&empty[wj], (unsigned)((ph - 1) & 1), 1, -1);
+        }
+        t4_mbar_arrive(&full[wj]);
+    }
+#ifdef MMPC_T4_PROFILE
+    if (blockIdx.x == 0 && (w == 0 || w == C::WORKERS - 1)) printf("[t4 bwd worker %d] %d rounds, %lld cycles\n", w, R, T4_CLK() - tw0);
+#endif
+}
+
+template <class M, class C>
+__device__ __noinline__ bool t4_bwd_serial(double* smem, int tid, double* rec_tile, int N, int base, int R) {
+    constexpr int NX = M::NX, NU = M::NU, I = C::I, S = C::S;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + C::SM_BAR);
+    unsigned long long* empty = full + C::NSLOT;
+    const int l = tid & 31, isub = l / C::LPI, a = l % C::LPI, q = tid >> 5;
+    const int ii = min(q * C::IPW + isub, I - 1);
+    const bool wr = q * C::IPW + isub < I;
+    T4Lane<C> ln;
+    ln.a = a;
+    MMPC_UNROLL for (int b = 0; b < S; ++b) ln.hoff[b] = (C::RB_H + trisym(a, b, S)) * I;
+    MMPC_UNROLL for (int b = 0; b < NX; ++b) ln.pxoff[b] = (C::PG_XX + trisym(a, b, NX)) * I;
+    T4Riccati<M> V;
+    MMPC_UNROLL for (int b = 0; b < NX; ++b) V.Pxx[b] = 0.0;
+    MMPC_UNROLL for (int b = 0; b < NU; ++b) V.Pxv[b] = 0.0;
+    V.px = 0.0;
+    MMPC_UNROLL for (int b = 0; b < NU * NU; ++b) V.Pvv[b] = 0.0;
+    MMPC_UNROLL for (int b = 0; b < NU; ++b) V.pv[b] = 0.0;
+    double R2[NU];
+    MMPC_UNROLL for (int b = 0; b < NU; ++b) R2[b] = smem[C::SM_CST + (C::CS_R + b) * I + ii];
+    double* xs = smem + C::SM_XS + (size_t)(q * C::IPW + isub) * C::XSI;
+    bool ok = true;
+    long long t_wait = 0, t_stage = 0;
+    for (int u = 0; u < R * C::NSLOT; ++u) {
+        const int k = N - 1 - u, sl = u % C::NSLOT;
+        const long long t0 = T4_CLK();
+        t4_mbar_wait(&full[sl], (unsigned)((base + u / C::NSLOT) & 1), 2, u);
+        const long long t1 = T4_CLK();
+        if (u < N) ok = t4_riccati_stage<M, C>(V, ln, smem + C::SM_REC + (size_t)sl * C::SLOT + ii, xs, R2, rec_tile + (size_t)k * C::RF * I + ii, wr) && ok;
+        t4_mbar_arrive_relaxed(&empty[sl]);
+        t_wait += t1 - t0; t_stage += T4_CLK() - t1;
+    }
+#ifdef MMPC_T4_PROFILE
+    if (blockIdx.x == 0 && tid == 0) printf("[t4 bwd serial] waiting %lld, stages %lld cycles (%d nodes)\n", t_wait, t_stage, N);
+#endif
+    return ok;
+}
+
+// returns (serial lanes) whether every G_uu was positive definite; residual norms of the iterate on the master lanes
+template <class M, class C>
+__device__ __forceinline__ bool t4_backward(const T3Ctx<M, C::I, 0>& c, double* smem, int tid, double delta_self, bool master, int inst, T3Norms& nrm_out,
+                                            double* rec_tile, int& ring_phase) {
+    constexpr int I = C::I;
+    const int N = c.N;
+    double* red = smem + C::SM_RED;
+    if (master) smem[C::SM_CST + C::CS_DELTA * I + inst] = delta_self;
     t4_sweep_entry<C>();
     const int R = (N + C::NSLOT - 1) / C::NSLOT, base = ring_phase;  // phases of every slot in this sweep
     ring_phase += R;
     bool ok = true;
     if (tid >= C::STHREADS) {
-        // ---------------- workers: group wj produces into slot wj ----------------
-        const int w = C::widx(tid), wi = w % I, wj = w / I;
-        if (w < C::WORKERS) {
-            const double delta = dl[wi];
-            T4Acc acc{0.0, 0.0, 0.0, 0.0, 0.0};
-            for (int r = 0; r < R; ++r) {
-                const int u = wj + r * C::CB, ph = base + r;  // u-th node of the sweep: k = N-1-u
-                if (u < N) {
-                    const int k = N - 1 - u;
-                    if (u + C::CB < N) t3_prefetch_node<M, C>(c, k - C::CB);
-                    t4_eval_node<M, C>(c, k, delta, smem + C::SM_REC + (size_t)wj * C::SLOT + wi, rec_tile + (size_t)k * C::RF * I + wi, acc, &empty[wj],
-                                       ph > 0 ? ((ph - 1) & 1) : -1);
-                } else if (ph > 0) {
-                    t4_mbar_wait(&empty[wj], (unsigned)((ph - 1) & 1), 1, -1);
-                }
-                t4_mbar_arrive(&full[wj]);
-            }
-            red[(0 * C::CB + wj) * I + wi] = acc.dual;
-            red[(1 * C::CB + wj) * I + wi] = acc.prim;
-            red[(2 * C::CB + wj) * I + wi] = acc.theta;
-            red[(3 * C::CB + wj) * I + wi] = acc.fval;
-            red[(4 * C::CB + wj) * I + wi] = acc.lam1;
-        }
+        if (C::widx(tid) < C::WORKERS) t4_bwd_worker<M, C>(c, smem, tid, rec_tile, base, R);
     } else if ((tid >> 5) < C::NSER) {
-        // ---------------- serial warps ----------------
-        const int l = tid & 31, isub = l / C::LPI, a = l % C::LPI, q = tid >> 5;
-        const int ii = min(q * C::IPW + isub, I - 1);
-        const bool wr = q * C::IPW + isub < I;
-        T4Lane<C> ln;
-        ln.a = a;
-        MMPC_UNROLL for (int b = 0; b < S; ++b) ln.hoff[b] = (C::RB_H + trisym(a, b, S)) * I;
-        MMPC_UNROLL for (int b = 0; b < NX; ++b) ln.pxoff[b] = (C::PG_XX + trisym(a, b, NX)) * I;
-        T4Riccati<M> V;
-        MMPC_UNROLL for (int b = 0; b < NX; ++b) V.Pxx[b] = 0.0;
-        MMPC_UNROLL for (int b = 0; b < NU; ++b) V.Pxv[b] = 0.0;
-        V.px = 0.0;
-        MMPC_UNROLL for (int b = 0; b < NU * NU; ++b) V.Pvv[b] = 0.0;
-        MMPC_UNROLL for (int b = 0; b < NU; ++b) V.pv[b] = 0.0;
-        double R2[NU];
-        MMPC_UNROLL for (int b = 0; b < NU; ++b) R2[b] = c.R[b];
-        double* xs = smem + C::SM_XS + (size_t)(q * C::IPW + isub) * C::XSI;
-        for (int u = 0; u < R * C::NSLOT; ++u) {
-            const int k = N - 1 - u, sl = u % C::NSLOT;
-            t4_mbar_wait(&full[sl], (unsigned)((base + u / C::NSLOT) & 1), 2, u);
-            if (u < N) ok = t4_riccati_stage<M, C>(V, ln, smem + C::SM_REC + (size_t)sl * C::SLOT + ii, xs, R2, rec_tile + (size_t)k * C::RF * I + ii, wr) && ok;
-            t4_mbar_arrive(&empty[sl]);
-        }
+        ok = t4_bwd_serial<M, C>(smem, tid, rec_tile, N, base, R);
     }
     t4_cta_sync();
     T3Norms o;
@@ -532,14 +581,160 @@ __device__ T4_SWEEP bool t4_backward(const T3Ctx<M, C::I, 0>& cin, double* smem,
 
 // ---- forward sweep: bulk-copied node records -> ring -> roll-out of the step (serial warps); merit of the trial point (workers) ----
 template <class M, class C>
-__device__ T4_SWEEP void t4_forward(const T3Ctx<M, C::I, 0>& cin, double* smem, int tid, bool master, int inst, T3Fwd& o_out, const double* rec_tile,
-                                    int& ring_phase) {
-    constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
+__device__ __noinline__ void t4_fwd_worker(const T3Ctx<M, C::I, 0>& cin, double* smem, int tid, const double* rec_tile, int base, int R) {
+    constexpr int NX = M::NX, S = C::S, I = C::I;
     const T3Ctx<M, C::I, 0> c = cin;
     const int N = c.N;
     double* red = smem + C::SM_RED;
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + C::SM_BAR);
     unsigned long long* empty = full + C::NSLOT;
+    const int w = C::widx(tid), wi = w % I, wj = w / I;
+    const bool act = smem[C::SM_INST + 2 * I + wi] != 0.0;
+    double f1 = 0.0, th1 = 0.0;
+    T3TrialBD bd;
+    bd.bar1 = 0.0; bd.amax = bd.az = 1.0; bd.full = true; bd.mu = 0.0; bd.tau = 0.99;
+    // Group wj brings the records of ITS nodes (k = wj, wj + CB, ...) into ITS slot: the record of the next round is
+    // requested right after the wait for "the roll-out has passed node k", which is also the slot's "empty" condition.
+    // Every thread of the group arrives on the slot's full barrier (count I, as in the backward sweep); the first one
+    // carries the transaction bytes of the bulk copy.
+    auto produce = [&](int r) {
+        const int kk = wj + r * C::CB;
+#ifdef MMPC_T4_NO_TMA
+        if (kk < N) {  // developer build: the node record is copied with plain loads / stores (bisecting aid)
+            const double* src = rec_tile + (size_t)kk * C::RF * I + wi;
+            double* dst = smem + C::SM_REC + (size_t)wj * C::SLOT + wi;
+            for (int f = 0; f < C::RF; ++f) dst[f * I] = src[f * I];
+        }
+        t4_mbar_arrive(&full[wj]);
+#else
+        if (wi == 0 && kk < N) {
+            t4_mbar_arrive_expect_tx(&full[wj], C::REC_BYTES);
+            t4_bulk_load(smem + C::SM_REC + (size_t)wj * C::SLOT, rec_tile + (size_t)kk * C::RF * I, C::REC_BYTES, &full[wj]);
+        } else {
+            t4_mbar_arrive(&full[wj]);
+        }
+#endif
+    };
+    const long long tw0 = T4_CLK();
+    long long t_merit = 0;
+    if (base > 0) t4_mbar_wait(&empty[wj], (unsigned)((base - 1) & 1), 3, -1);  // the slot's last use of the previous sweep (long complete)
+    produce(0);
+    for (int r = 0; r < R; ++r) {
+        const int k = wj + r * C::CB;
+        if (k < N) {
+            MMPC_UNROLL for (int a = 0; a < S + NX; ++a) t3_prefetch(c.V + ((size_t)k * S + a) * I);  // iterate rows of the merit evaluation -> L1
+            t3_prefetch(c.traj + (size_t)k * NX);
+        }
+        t4_mbar_wait(&empty[wj], (unsigned)((base + r) & 1), 3, k);  // the roll-out has passed node k: dz_k, dz_{k+1} are written
+        if (r + 1 < R) produce(r + 1);
+        const long long tm0 = T4_CLK();
+        if (k < N) t3_trial_node<M, C>(c, k, 1.0, f1, th1, bd, !act);
+        t_merit += T4_CLK() - tm0;
+    }
+#ifdef MMPC_T4_PROFILE
+    if (blockIdx.x == 0 && (w == 0 || w == C::WORKERS - 1)) printf("[t4 fwd worker %d] total %lld, merit %lld cycles\n", w, T4_CLK() - tw0, t_merit);
+#endif
+    red[(0 * C::CB + wj) * I + wi] = f1;
+    red[(1 * C::CB + wj) * I + wi] = th1;
+}
+
+struct T4FwdSerial {
+    double gradf_d, lam_inf;
+    bool finite;
+};
+
+template <class M, class C>
+__device__ __noinline__ void t4_fwd_serial(double* smem, int tid, double* DV, double* LAMN, int N, int base, int R, T4FwdSerial& out) {
+    constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + C::SM_BAR);
+    unsigned long long* empty = full + C::NSLOT;
+    const int l = tid & 31, isub = l / C::LPI, a = l % C::LPI, q = tid >> 5;
+    const int ii = min(q * C::IPW + isub, I - 1);
+    const bool wr = q * C::IPW + isub < I;
+    const bool act = smem[C::SM_INST + 2 * I + ii] != 0.0;
+    int pxoff[NX];
+    MMPC_UNROLL for (int b = 0; b < NX; ++b) pxoff[b] = (C::RF_P + C::PG_XX + trisym(a, b, NX)) * I;
+    double dx[NX], dv[NU];
+    MMPC_UNROLL for (int b = 0; b < NX; ++b) dx[b] = 0.0;
+    MMPC_UNROLL for (int b = 0; b < NU; ++b) dv[b] = 0.0;
+    double gradf_d = 0.0, lam_inf = 0.0;
+    bool finite = true;
+    long long t_wait = 0;
+    const long long ts0 = T4_CLK();
+    for (int k = 0; k < R * C::NSLOT; ++k) {
+        const int sl = k % C::NSLOT;
+        const long long t0 = T4_CLK();
+        t4_mbar_wait(&full[sl], (unsigned)((base + k / C::NSLOT) & 1), 4, k);
+        t_wait += T4_CLK() - t0;
+        if (k >= N) {  // slot without a node in the last round: empty hand-shake
+            t4_mbar_arrive(&empty[sl]);
+            continue;
+        }
+        const double* rp = smem + C::SM_REC + (size_t)sl * C::SLOT + ii;
+        // all loads of the stage first (their latencies overlap), then the two short dependent chains du -> dx+
+        double K0[NU], KX[NU * NX], KV[NU * NU], Cc[NX], FXv[C::NFX], FUv[C::NFU], Qt[C::N2], Pr[NX], Pv[NU];
+        MMPC_UNROLL for (int p = 0; p < NU; ++p) K0[p] = rp[(C::RF_K + C::KG_K0 + p) * I];
+        MMPC_UNROLL for (int p = 0; p < NU * NX; ++p) KX[p] = rp[(C::RF_K + C::KG_KX + p) * I];
+        MMPC_UNROLL for (int p = 0; p < NU * NU; ++p) KV[p] = rp[(C::RF_K + C::KG_KV + p) * I];
+        MMPC_UNROLL for (int p = 0; p < NX; ++p) Cc[p] = rp[(C::FG_C + p) * I];
+        MMPC_UNROLL for (int p = 0; p < C::NFX; ++p) FXv[p] = rp[(C::FG_FX + p) * I];
+        MMPC_UNROLL for (int p = 0; p < C::NFU; ++p) FUv[p] = rp[(C::FG_FU + p) * I];
+        MMPC_UNROLL for (int p = 0; p < C::N2; ++p) Qt[p] = rp[(C::FG_Q + p) * I];
+        const double pxa = rp[(C::RF_P + C::PG_X + a) * I];
+        MMPC_UNROLL for (int p = 0; p < NX; ++p) Pr[p] = rp[pxoff[p]];
+        MMPC_UNROLL for (int p = 0; p < NU; ++p) Pv[p] = rp[(C::RF_P + C::PG_XV + a * NU + p) * I];
+        double du[NU], dxn[NX];
+        MMPC_UNROLL for (int p = 0; p < NU; ++p) {
+            double t = K0[p], t2 = 0.0;
+            MMPC_UNROLL for (int r = 0; r < NX; ++r) t = fma(KX[p * NX + r], dx[r], t);
+            MMPC_UNROLL for (int r = 0; r < NU; ++r) t2 = fma(KV[p * NU + r], dv[r], t2);
+            du[p] = t + t2;
+        }
+        MMPC_UNROLL for (int p = 0; p < NX; ++p) {
+            double t = Cc[p], t2 = 0.0;
+            MMPC_UNROLL for (int r = 0; r < NX; ++r) if (T4_FXNZ(p, r)) t = fma(FXv[T4_FXSLOT(p * NX + r)], dx[r], t);
+            MMPC_UNROLL for (int r = 0; r < NU; ++r) if (T4_FUNZ(p, r)) t2 = fma(FUv[T4_FUSLOT(p * NU + r)], du[r], t2);
+            dxn[p] = t + t2;
+        }
+        // directional derivative of the objective: q~ . (dx, dv, du)  (every lane of the instance computes it; the master's copy is used)
+        MMPC_UNROLL for (int p = 0; p < NX; ++p) gradf_d = fma(Qt[p], dx[p], gradf_d);
+        MMPC_UNROLL for (int p = 0; p < NU; ++p) {
+            gradf_d = fma(Qt[NX + p], dv[p], gradf_d);
+            gradf_d = fma(Qt[S + p], du[p], gradf_d);
+        }
+        // lam_k+ = (P_{k+1} (dx_{k+1}, du_k) + p_{k+1})_x : entry a in lane a
+        double lam = pxa;
+        MMPC_UNROLL for (int r = 0; r < NX; ++r) lam = fma(Pr[r], dxn[r], lam);
+        MMPC_UNROLL for (int r = 0; r < NU; ++r) lam = fma(Pv[r], du[r], lam);
+        const double dxa = t4_pick<NX>(dxn, a);
+        if (wr) {
+            if (act) LAMN[((size_t)k * NX + a) * I] = lam;
+            DV[((size_t)(k + 1) * S + a) * I] = dxa;
+            if (a < NU) DV[((size_t)k * S + NX + a) * I] = t4_pick<NU>(du, a);
+        }
+        lam_inf = fmax(lam_inf, fabs(lam));
+        finite = finite && isfinite(lam) && isfinite(dxa);
+        MMPC_UNROLL for (int b = 0; b < NX; ++b) dx[b] = dxn[b];
+        MMPC_UNROLL for (int b = 0; b < NU; ++b) dv[b] = du[b];
+        t4_mbar_arrive(&empty[sl]);
+    }
+#ifdef MMPC_T4_PROFILE
+    if (blockIdx.x == 0 && tid == 0) printf("[t4 fwd serial] total %lld, waiting %lld cycles\n", T4_CLK() - ts0, t_wait);
+#endif
+    // combine the rows of the instance (lanes a = 0..LPI-1 are adjacent)
+    MMPC_UNROLL for (int m = 1; m < C::LPI; m <<= 1) {
+        lam_inf = fmax(lam_inf, __shfl_xor_sync(0xffffffffu, lam_inf, m));
+        finite = __shfl_xor_sync(0xffffffffu, (int)finite, m) && finite;
+    }
+    out.gradf_d = gradf_d; out.lam_inf = lam_inf; out.finite = finite;
+}
+
+template <class M, class C>
+__device__ __forceinline__ void t4_forward(const T3Ctx<M, C::I, 0>& c, double* smem, int tid, bool master, int inst, T3Fwd& o_out, const double* rec_tile,
+                                           int& ring_phase) {
+    constexpr int I = C::I;
+    const int N = c.N;
+    double* red = smem + C::SM_RED;
     T3Fwd o;
     o.gradf_d = o.lam_inf = o.f1 = o.th1 = o.bar1 = 0.0;
     o.amax = o.az = 1.0;
@@ -548,110 +743,11 @@ __device__ T4_SWEEP void t4_forward(const T3Ctx<M, C::I, 0>& cin, double* smem, 
     const int R = (N + C::NSLOT - 1) / C::NSLOT, base = ring_phase;
     ring_phase += R;
     if (tid >= C::STHREADS) {
-        const int w = C::widx(tid), wi = w % I, wj = w / I;
-        if (w < C::WORKERS) {
-            const bool act = smem[C::SM_INST + 2 * I + wi] != 0.0;
-            double f1 = 0.0, th1 = 0.0;
-            T3TrialBD bd;
-            bd.bar1 = 0.0; bd.amax = bd.az = 1.0; bd.full = true; bd.mu = 0.0; bd.tau = 0.99;
-            // Group wj brings the records of ITS nodes (k = wj, wj + CB, ...) into ITS slot: the record of the next round is
-            // requested right after the wait for "the roll-out has passed node k", which is also the slot's "empty" condition.
-            // Every thread of the group arrives on the slot's full barrier (count I, as in the backward sweep); the first one
-            // carries the transaction bytes of the bulk copy.
-            auto produce = [&](int r) {
-                const int kk = wj + r * C::CB;
-#ifdef MMPC_T4_NO_TMA
-                if (kk < N) {  // developer build: the node record is copied with plain loads / stores (bisecting aid)
-                    const double* src = rec_tile + (size_t)kk * C::RF * I + wi;
-                    double* dst = smem + C::SM_REC + (size_t)wj * C::SLOT + wi;
-                    for (int f = 0; f < C::RF; ++f) dst[f * I] = src[f * I];
-                }
-                t4_mbar_arrive(&full[wj]);
-#else
-                if (wi == 0 && kk < N) {
-                    t4_mbar_arrive_expect_tx(&full[wj], C::REC_BYTES);
-                    t4_bulk_load(smem + C::SM_REC + (size_t)wj * C::SLOT, rec_tile + (size_t)kk * C::RF * I, C::REC_BYTES, &full[wj]);
-                } else {
-                    t4_mbar_arrive(&full[wj]);
-                }
-#endif
-            };
-            if (base > 0) t4_mbar_wait(&empty[wj], (unsigned)((base - 1) & 1), 3, -1);  // the slot's last use of the previous sweep (long complete)
-            produce(0);
-            for (int r = 0; r < R; ++r) {
-                const int k = wj + r * C::CB;
-                if (k < N) {
-                    MMPC_UNROLL for (int a = 0; a < S + NX; ++a) t3_prefetch(c.V + ((size_t)k * S + a) * I);  // iterate rows of the merit evaluation -> L1
-                    t3_prefetch(c.traj + (size_t)k * NX);
-                }
-                t4_mbar_wait(&empty[wj], (unsigned)((base + r) & 1), 3, k);  // the roll-out has passed node k: dz_k, dz_{k+1} are written
-                if (r + 1 < R) produce(r + 1);
-                if (k < N) t3_trial_node<M, C>(c, k, 1.0, f1, th1, bd, !act);
-            }
-            red[(0 * C::CB + wj) * I + wi] = f1;
-            red[(1 * C::CB + wj) * I + wi] = th1;
-        }
+        if (C::widx(tid) < C::WORKERS) t4_fwd_worker<M, C>(c, smem, tid, rec_tile, base, R);
     } else if ((tid >> 5) < C::NSER) {
-        const int l = tid & 31, isub = l / C::LPI, a = l % C::LPI, q = tid >> 5;
-        const int ii = min(q * C::IPW + isub, I - 1);
-        const bool wr = q * C::IPW + isub < I;
-        const bool act = smem[C::SM_INST + 2 * I + ii] != 0.0;
-        int pxoff[NX];
-        MMPC_UNROLL for (int b = 0; b < NX; ++b) pxoff[b] = (C::RF_P + C::PG_XX + trisym(a, b, NX)) * I;
-        double dx[NX], dv[NU];
-        MMPC_UNROLL for (int b = 0; b < NX; ++b) dx[b] = 0.0;
-        MMPC_UNROLL for (int b = 0; b < NU; ++b) dv[b] = 0.0;
-        // this thread's instance inside the tile arrays (the context's pointers belong to the calling thread's instance: same thing)
-        for (int k = 0; k < R * C::NSLOT; ++k) {
-            const int sl = k % C::NSLOT;
-            t4_mbar_wait(&full[sl], (unsigned)((base + k / C::NSLOT) & 1), 4, k);
-            if (k >= N) {  // slot without a node in the last round: empty hand-shake
-                t4_mbar_arrive(&empty[sl]);
-                continue;
-            }
-            const double* rp = smem + C::SM_REC + (size_t)sl * C::SLOT + ii;
-#define T4_F(f) rp[(f) * I]
-            double du[NU], dxn[NX];
-            MMPC_UNROLL for (int p = 0; p < NU; ++p) {
-                double t = T4_F(C::RF_K + C::KG_K0 + p);
-                MMPC_UNROLL for (int r = 0; r < NX; ++r) t = fma(T4_F(C::RF_K + C::KG_KX + p * NX + r), dx[r], t);
-                MMPC_UNROLL for (int r = 0; r < NU; ++r) t = fma(T4_F(C::RF_K + C::KG_KV + p * NU + r), dv[r], t);
-                du[p] = t;
-            }
-            MMPC_UNROLL for (int p = 0; p < NX; ++p) {
-                double t = T4_F(C::FG_C + p);
-                MMPC_UNROLL for (int r = 0; r < NX; ++r) if (T4_FXNZ(p, r)) t = fma(T4_F(C::FG_FX + T4_FXSLOT(p * NX + r)), dx[r], t);
-                MMPC_UNROLL for (int r = 0; r < NU; ++r) if (T4_FUNZ(p, r)) t = fma(T4_F(C::FG_FU + T4_FUSLOT(p * NU + r)), du[r], t);
-                dxn[p] = t;
-            }
-            // directional derivative of the objective: q~ . (dx, dv, du)  (every lane of the instance computes it; the master's copy is used)
-            MMPC_UNROLL for (int p = 0; p < NX; ++p) o.gradf_d = fma(T4_F(C::FG_Q + p), dx[p], o.gradf_d);
-            MMPC_UNROLL for (int p = 0; p < NU; ++p) {
-                o.gradf_d = fma(T4_F(C::FG_Q + NX + p), dv[p], o.gradf_d);
-                o.gradf_d = fma(T4_F(C::FG_Q + S + p), du[p], o.gradf_d);
-            }
-            // lam_k+ = (P_{k+1} (dx_{k+1}, du_k) + p_{k+1})_x : entry a in lane a
-            double lam = rp[(C::RF_P + C::PG_X + a) * I];
-            MMPC_UNROLL for (int r = 0; r < NX; ++r) lam = fma(rp[pxoff[r]], dxn[r], lam);
-            MMPC_UNROLL for (int r = 0; r < NU; ++r) lam = fma(rp[(C::RF_P + C::PG_XV + a * NU + r) * I], du[r], lam);
-#undef T4_F
-            const double dxa = t4_pick<NX>(dxn, a);
-            if (wr) {
-                if (act) c.LAMN[((size_t)k * NX + a) * I] = lam;
-                c.DV[((size_t)(k + 1) * S + a) * I] = dxa;
-                if (a < NU) c.DV[((size_t)k * S + NX + a) * I] = t4_pick<NU>(du, a);
-            }
-            o.lam_inf = fmax(o.lam_inf, fabs(lam));
-            o.finite = o.finite && isfinite(lam) && isfinite(dxa);
-            MMPC_UNROLL for (int b = 0; b < NX; ++b) dx[b] = dxn[b];
-            MMPC_UNROLL for (int b = 0; b < NU; ++b) dv[b] = du[b];
-            t4_mbar_arrive(&empty[sl]);
-        }
-        // combine the rows of the instance (lanes a = 0..LPI-1 are adjacent)
-        MMPC_UNROLL for (int m = 1; m < C::LPI; m <<= 1) {
-            o.lam_inf = fmax(o.lam_inf, __shfl_xor_sync(0xffffffffu, o.lam_inf, m));
-            o.finite = __shfl_xor_sync(0xffffffffu, (int)o.finite, m) && o.finite;
-        }
+        T4FwdSerial fs;
+        t4_fwd_serial<M, C>(smem, tid, c.DV, c.LAMN, N, base, R, fs);
+        o.gradf_d = fs.gradf_d; o.lam_inf = fs.lam_inf; o.finite = fs.finite;
     }
     t4_cta_sync();
     if (master) {
@@ -671,6 +767,9 @@ __global__ void __launch_bounds__(T4<M, I_>::THREADS, 1) solve_kernel_t4(mmpc_pr
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, tile = io.b0 / I + blockIdx.x;  // b0 is a multiple of the tile width (the ABI layer cuts sub-batches on tile boundaries)
     const bool serial = tid < C::STHREADS;
+#ifdef MMPC_T4_PROFILE
+    const long long t_entry = T4_CLK();
+#endif
     t4_ring_init<C>(smem, tid);
     int ring_phase = 0;  // phases every ring slot has completed so far (same value in every thread)
     // register budgets by role: warpgroup 0 = serial warps, warpgroups 1-3 = evaluators
@@ -703,6 +802,12 @@ __global__ void __launch_bounds__(T4<M, I_>::THREADS, 1) solve_kernel_t4(mmpc_pr
         c.Rm[a] = W.Rmw[(size_t)a * W.Bp + bi];
         c.uinit[a] = io.control[(size_t)bi * NU + a];
     }
+    if (worker && j == 0) {  // per-instance constants of the evaluators
+        double* cs = smem + C::SM_CST + i;
+        MMPC_UNROLL for (int a = 0; a < NX; ++a) cs[(C::CS_Q + a) * I] = c.Q[a];
+        MMPC_UNROLL for (int a = 0; a < NU; ++a) { cs[(C::CS_R + a) * I] = c.R[a]; cs[(C::CS_RM + a) * I] = c.Rm[a]; cs[(C::CS_U0 + a) * I] = c.uinit[a]; }
+        cs[C::CS_DELTA * I] = 0.0;
+    }
     // ---- start point (ModelControl.cpp:28-50,68 cold; :161 warm), x_0 pinned (:144-145) ----
     const bool warm = io.warm_start && W.have_warm;
     if (worker) {
@@ -732,6 +837,10 @@ __global__ void __launch_bounds__(T4<M, I_>::THREADS, 1) solve_kernel_t4(mmpc_pr
     double* sh_flag = smem + C::SM_INST + 2 * I;
     const int nfree = N * S, ncon = N * NX;
     bool expect_converged = false;
+#ifdef MMPC_T4_PROFILE
+    const long long tk0 = T4_CLK();
+    long long tp_res = 0, tp_bwd = 0, tp_fwd = 0, tp_post = 0;
+#endif
     for (it = 0;; ++it) {
         T3Norms nrm;
         double delta = 0.0;
@@ -740,7 +849,13 @@ __global__ void __launch_bounds__(T4<M, I_>::THREADS, 1) solve_kernel_t4(mmpc_pr
             // every instance of the tile that still iterates took a full Newton step from a small KKT error: test the new iterate
             // with the cheap first-derivative residual sweep; the full sweep runs only if some instance fails (as in T3)
             T3NormsBD nb;
+#ifdef MMPC_T4_PROFILE
+            const long long tr0 = T4_CLK();
+#endif
             t3_residuals<M, C>(c, smem, tid, nb);
+#ifdef MMPC_T4_PROFILE
+            tp_res += T4_CLK() - tr0;
+#endif
             // t3_residuals reduces into the threads tid < I; here the per-instance state lives in the master lanes
             double* rr = smem + C::SM_RED;
             if (tid < I) { rr[0 * I + tid] = nb.dual_inf; rr[1 * I + tid] = nb.prim_inf; rr[2 * I + tid] = nb.fval; rr[3 * I + tid] = nb.lam_l1; }
@@ -756,7 +871,13 @@ __global__ void __launch_bounds__(T4<M, I_>::THREADS, 1) solve_kernel_t4(mmpc_pr
             }
             if (!__syncthreads_or(active)) break;
         }
+#ifdef MMPC_T4_PROFILE
+        const long long tb0 = T4_CLK();
+#endif
         ok = t4_backward<M, C>(c, smem, tid, delta, master, sinst, nrm, rec_tile, ring_phase);
+#ifdef MMPC_T4_PROFILE
+        tp_bwd += T4_CLK() - tb0;
+#endif
         if (active) {
             const double sd = fmax(100.0, nrm.lam_l1 / (double)(nfree + ncon)) / 100.0;  // IPOPT s_d, s_max = 100 [upstream]
             err = fmax(nrm.dual_inf / sd, nrm.prim_inf);
@@ -785,7 +906,14 @@ __global__ void __launch_bounds__(T4<M, I_>::THREADS, 1) solve_kernel_t4(mmpc_pr
         if (master) sh_flag[sinst] = active ? 1.0 : 0.0;  // which instances still iterate: read by the forward sweep
         if (!__syncthreads_or(active)) break;
         T3Fwd fo;
+#ifdef MMPC_T4_PROFILE
+        const long long tf0 = T4_CLK();
+#endif
         t4_forward<M, C>(c, smem, tid, master, sinst, fo, rec_tile, ring_phase);
+#ifdef MMPC_T4_PROFILE
+        const long long tf1 = T4_CLK();
+        tp_fwd += tf1 - tf0;
+#endif
         if (active && !(fo.finite && isfinite(fo.f1))) { status = MMPC_SOLVE_NUMERICAL; active = false; }
         nu_merit = fmax(nu_merit, 1.1 * fo.lam_inf + 1e-8);
         const double m0 = nrm.fval + nu_merit * nrm.theta;
@@ -830,7 +958,13 @@ __global__ void __launch_bounds__(T4<M, I_>::THREADS, 1) solve_kernel_t4(mmpc_pr
             const bool expect = alpha == 1.0 && (P.is_linear || err <= T3_EXPECT_CONVERGED_BELOW);
             expect_converged = !__syncthreads_or(active && !expect);
         }
+#ifdef MMPC_T4_PROFILE
+        tp_post += T4_CLK() - tf1;
+#endif
     }
+#ifdef MMPC_T4_PROFILE
+    const long long tk1 = T4_CLK();
+#endif
     // ---- outputs: the reference's V layout, instance-major.  The warm start lives in LAM2: after an odd number of accepted
     // steps the multipliers are copied back there ----
     double* const Lcan = W.LAM2 + (size_t)tile * I * Mc + i;
@@ -855,6 +989,12 @@ __global__ void __launch_bounds__(T4<M, I_>::THREADS, 1) solve_kernel_t4(mmpc_pr
             }
         }
     }
+#ifdef MMPC_T4_PROFILE
+    __syncthreads();
+    if (blockIdx.x == 0 && tid == 0)
+        printf("[t4 kernel] prologue %lld  loop %lld (residual sweeps %lld, backward %lld, forward %lld, line search + step %lld)  epilogue %lld cycles, %d iterations\n",
+               tk0 - t_entry, tk1 - tk0, tp_res, tp_bwd, tp_fwd, tp_post, T4_CLK() - tk1, it);
+#endif
     if (valid && master && io.stats) {
         mmpc_stats s;
         s.objective = fval; s.kkt_error = err; s.mu = 0.0; s.iterations = it_done; s.status = status;
