@@ -4,7 +4,7 @@ import os, sys
 import numpy as np, torch
 import mahi_mpc_b200.api as api
 from mahi_mpc_b200 import workload
-N = int(sys.argv[1]); variant = int(sys.argv[2]); dev = torch.device("cuda", 0)
+N = int(sys.argv[1]); variant = int(sys.argv[2], 0); dev = torch.device("cuda", 0)
 for B in [int(v) for v in sys.argv[3:]]:
     x0, up, traj = workload.synthetic_batch(4, 2, N, 0.002, B)
     Q, R, Rm = workload.default_weights(4, 2)

@@ -1,0 +1,8 @@
+mkdir -p gpurun_out
+for cfg in "0x104 25 3" "0x204 50 20" "0x304 50 40" "0x104 200 30" "4 50 4096 1e-5"; do timeout 120 python -m tools.t4_check $cfg 2>&1 | grep -E "variant|rror" || echo "FAILED/TIMEOUT $cfg rc=$?"; done
+timeout 300 python -m tools.dev_time 50 3 4096 2>&1 | tail -1
+timeout 300 python -m tools.dev_time 50 4 32 1184 2048 4096 8192 2>&1 | tail -5
+timeout 300 python -m tools.dev_time 50 0x304 4096 2>&1 | tail -1
+timeout 300 python -m tools.dev_time 50 0x104 4096 2>&1 | tail -1
+python -m tools.rebuild_unit builtin_double_pendulum_t4 -DMMPC_T4_PROFILE -DMMPC_T3_PROFILE_SWEEPS > /dev/null 2>&1
+timeout 100 python -m tools.t4_prof 4 50 4096 2>&1 | tail -24

@@ -1,0 +1,5 @@
+for v in 0x304; do timeout 300 python -m tools.dev_time 50 $v 4096 2>&1 | tail -1; done
+python -m tools.rebuild_unit builtin_double_pendulum_t4 -DMMPC_T4_PROFILE > /dev/null 2>&1
+for v in 0x304; do timeout 100 python -m tools.t4_prof $v 50 4096 2>&1 | tail -2; done
+python -m tools.rebuild_unit builtin_double_pendulum_t4 -DMMPC_T4_PROFILE -DMMPC_T3_PROFILE_SWEEPS > /dev/null 2>&1
+for v in 0x304; do echo "== $v"; timeout 100 python -m tools.t4_prof $v 50 4096 2>&1 | tail -5; done
