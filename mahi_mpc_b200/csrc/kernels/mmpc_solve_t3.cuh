@@ -67,6 +67,8 @@ struct T3 {
     static constexpr int FG_FX = 0, FG_FU = NFX, FG_C = FG_FU + NFU, FG_Q = FG_C + NX, FG_GN = FG_Q + N2, FG = FG_Q + N2 + (BD ? NX : 0);
     static constexpr int KG_KX = 0, KG_KV = NU * NX, KG_K0 = KG_KV + NU * NU, KG = KG_K0 + NU;
     static constexpr int PG_XX = 0, PG_XV = NPX, PG_X = PG_XV + NX * NU, PG = PG_X + NX;
+    // node strides of the three global record arrays (T4 interleaves them into one record per node and overrides these)
+    static constexpr int FG_NS = FG, KG_NS = KG, PG_NS = PG;
     // forward record (shared) = FG | KG | PG
     static constexpr int RF_K = FG, RF_P = FG + KG, RF = FG + KG + PG;
     static constexpr int BUF = (CB * RB > CF * RF ? CB * RB : CF * RF) * I;  // one record buffer (two are used)
@@ -216,7 +218,7 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I, C::MODE>& c, i
     double F[NX], Fx[NX * NX], Fu[NX * NU], H[NH];
     c.template step<2>(x, u, wq, r, lam, F, Fx, Fu, H);
     double* const recp = rec + (size_t)j * C::RB * I + i;
-    double* const fgp = fg_tile + (size_t)k * C::FG * I + i;
+    double* const fgp = fg_tile + (size_t)k * C::FG_NS * I + i;
 #define T3_REC(f) recp[(f) * I]
 #define T3_FG(f, v) T3_ST(&fgp[(f) * I], (v))
     double qe[NX], dual = 0.0, prim = 0.0, theta = 0.0, fval = 0.0, lam1 = 0.0;
@@ -335,7 +337,11 @@ __device__ __forceinline__ bool t3_riccati_stage(T3Riccati<M>& V, const double* 
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
         MMPC_UNROLL for (int b = 0; b < NX; ++b) {
             double t = 0.0;
-            MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FXNZ(q, b)) t = fma(V.Pxx[a * NX + q], Fx[q * NX + b], t);
+            bool first = true;  // folds at compile time: the first product initialises the accumulator (no zeroing, no fma with 0)
+            MMPC_UNROLL for (int q = 0; q < NX; ++q) if (T3_FXNZ(q, b)) {
+                t = first ? V.Pxx[a * NX + q] * Fx[q * NX + b] : fma(V.Pxx[a * NX + q], Fx[q * NX + b], t);
+                first = false;
+            }
             PA[a * NX + b] = t;
         }
         MMPC_UNROLL for (int b = 0; b < NU; ++b) {
@@ -422,8 +428,8 @@ __device__ __forceinline__ bool t3_riccati_stage(T3Riccati<M>& V, const double* 
             V.Pxx[b * NX + a] = t;
         }
         MMPC_UNROLL for (int b = 0; b < NU; ++b) {
-            double t = 0.0;
-            MMPC_UNROLL for (int l = 0; l < NU; ++l) t = fma(Gxu[a * NU + l], Kv[l * NU + b], t);
+            double t = Gxu[a * NU + 0] * Kv[0 * NU + b];
+            MMPC_UNROLL for (int l = 1; l < NU; ++l) t = fma(Gxu[a * NU + l], Kv[l * NU + b], t);
             V.Pxv[a * NU + b] = t;
         }
         double t = gx[a];
@@ -504,7 +510,7 @@ __device__ __noinline__ bool t3_backward(const T3Ctx<M, C::I, C::MODE>& cin, dou
                 const double* red = smem + C::SM_RED + (ch & 1) * C::REDBUF;
                 for (int s = kn - 1; s >= 0; --s) {
                     const int k = k0 + s;
-                    ok = t3_riccati_stage<M, C>(V, rec, s, tid, R, kg_tile + (size_t)k * C::KG * I + tid, pg_tile + (size_t)k * C::PG * I + tid) && ok;
+                    ok = t3_riccati_stage<M, C>(V, rec, s, tid, R, kg_tile + (size_t)k * C::KG_NS * I + tid, pg_tile + (size_t)k * C::PG_NS * I + tid) && ok;
                     n_dual = fmax(n_dual, red[(0 * C::CB + s) * I + tid]);
                     n_prim = fmax(n_prim, red[(1 * C::CB + s) * I + tid]);
                     n_theta += red[(2 * C::CB + s) * I + tid];

@@ -46,34 +46,84 @@ struct T4 : T3<M, I_, CB_, CF_, 0, RK_> {
     __device__ static __forceinline__ bool is_worker(int tid) { return SK_ ? (((tid >> 5) & 3) != 0) : tid >= 32; }
     __device__ static __forceinline__ int widx(int tid) { return SK_ ? tid - 32 * (1 + (tid >> 7)) : tid - 32; }
     __device__ static __forceinline__ int slot_of(int g) { return SK_ ? g : Base::slot_of(g); }
-    // forward-sweep record in shared memory: Fx | Fu | c (the leading fields of the global FG record) | gains (KG)
-    static constexpr int RS_F = Base::FG_Q, RS_K = RS_F, RS = RS_F + Base::KG;
-    // shared-memory map: T3's, with record buffers sized for the backward record and THIS forward record (these shadow the
+    // ONE global record per node and tile, [field][instance]:  Fx | Fu | c | gains  ||  q~ | value-function rows  -- the first
+    // REC_C rows are what the forward roll-out needs (chain part), the other REC_P rows what the post-processing of the step
+    // needs (post part): each part of a node is one contiguous block, moved by one bulk copy (TMA).  T3's sweeps write the
+    // record through the same field names: FG_Q (where q~ starts) and the node strides are overridden accordingly.
+    static constexpr int RS_F = Base::FG_C + Base::NX;  // Fx | Fu | c
+    static constexpr int REC_C = RS_F + Base::KG, REC_P = Base::N2 + Base::PG, REC = REC_C + REC_P;
+    static constexpr int FG_Q = REC_C, FG_NS = REC, KG_NS = REC, PG_NS = REC;
+    static constexpr int REC_K = RS_F, REC_PG = REC_C + Base::N2;  // row offsets of the gains and the value-function rows
+    // Forward sweep, shared memory (an overlay of the backward sweep's record buffers).  Per chunk parity:
+    //   chain part  CF x REC_C x I
+    //   post part   CF x REC_P x I
+    //   dz          (CF + 1) x S x I   slot 0 = (du, dx) entering the chunk, slot s + 1 = (du_k, dx_{k+1}) of its node s
+    static constexpr int RC = REC_C, RC_K = RS_F, RP_Q = 0, RP_P = Base::N2, RP = REC_P;
+    static constexpr int FW_CHAIN = 0, FW_POST = CF_ * RC * I_, FW_DZ = FW_POST + CF_ * RP * I_, FWD = FW_DZ + (CF_ + 1) * Base::S * I_;
+    // shared-memory map: T3's, with record buffers sized for the backward record and THIS forward layout (these shadow the
     // base's constants: the sweeps T4 borrows from T3 read them through C::)
-    static constexpr int BUF = (CB_ * Base::RB > CF_ * RS ? CB_ * Base::RB : CF_ * RS) * I_;
-    static constexpr int SM_REC = 0, SM_RED = 2 * BUF, SM_INST = SM_RED + 2 * Base::REDBUF, SM_END = SM_INST + 6 * I_;
+    static constexpr int BUF = CB_ * Base::RB * I_ > FWD ? CB_ * Base::RB * I_ : FWD;
+    static constexpr int SM_REC = 0, SM_RED = 2 * BUF, SM_INST = SM_RED + 2 * Base::REDBUF, SM_BAR = SM_INST + 6 * I_, SM_END = SM_BAR + 4;
     static constexpr size_t SMEM_BYTES = sizeof(double) * SM_END;
+    static_assert((I_ % 2) == 0, "bulk copies move multiples of 16 bytes: rows of an even number of instances");
 };
 
 #ifdef MMPC_T4_PROFILE
 __device__ long long t4_dbg[16];
 #define T4_STAMP(slot, t_from) do { if (blockIdx.x == 0 && tid == 0) { const long long t_now = clock64(); t4_dbg[slot] += t_now - (t_from); (t_from) = t_now; } } while (0)
+#define T4_STAMPW(slot, t_from) do { if (blockIdx.x == 0 && tid == 32) { const long long t_now = clock64(); t4_dbg[slot] += t_now - (t_from); (t_from) = t_now; } } while (0)
 #else
 #define T4_STAMP(slot, t_from) do { } while (0)
+#define T4_STAMPW(slot, t_from) do { } while (0)
 #endif
 
 __device__ __forceinline__ void t4_discard_l2(const void* line128) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(line128) : "memory"); }
+
+// ---- mbarrier / bulk-copy primitives (PTX ISA 8.x, sm_90+) ---------------------------------------------------------
+__device__ __forceinline__ unsigned t4_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void t4_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t4_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void t4_mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(t4_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void t4_mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "T4_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra T4_DONE;\n"
+        "bra T4_WAIT;\n"
+        "T4_DONE:\n"
+        "}\n" ::"r"(t4_smem_u32(bar)),
+        "r"(parity), "r"(0x989680u)  // suspend-time hint: the waiting warp sleeps in hardware instead of polling shared memory
+        : "memory");
+}
+// one contiguous block global -> shared through the TMA unit; completion (bytes) is signalled on `bar`
+__device__ __forceinline__ void t4_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(t4_smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(t4_smem_u32(bar))
+                 : "memory");
+}
+// generic-proxy accesses (st.shared / ld.shared of the record buffers, st.global of the node records) are ordered before the
+// async proxy (the bulk copies) touches the same bytes
+__device__ __forceinline__ void t4_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void t4_fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 struct T4Fwd {
     double gradf_d, lam_inf;
     bool finite;
 };
 
-// forward sweep for the tile.  Step ch of the pipeline: warp 0 rolls the Newton step through chunk ch (records in buffer
-// ch & 1); the workers stage chunk ch+1 into the other buffer and post-process chunk ch-1 (whose dz is in global memory).
+// Forward sweep for the tile.  Step ch of the pipeline (one CTA barrier per step):
+//   TMA     chain part of chunk ch+1 and post part of chunk ch -> shared memory (issued by the first worker thread)
+//   warp 0  rolls the Newton step through chunk ch: lane i = instance i, chain part of parity ch & 1 -> dz (shared + global)
+//   workers post-process chunk ch-1, thread = (instance, node): lam+, grad f . d, z += dz -- from shared memory but for z
+// `phase` counts the completed uses of the four mbarriers (chain / post x parity): they are initialised once per kernel.
 template <class M, class C>
 __device__ __noinline__ void t4_forward(const T3Ctx<M, C::I, C::MODE>& cin, double* smem, int tid, T4Fwd& o_out, const double* fg_tile,
-                                        const double* kg_tile, const double* pg_tile) {
+                                        const double* kg_tile, const double* pg_tile, unsigned (&phase)[4]) {
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I, N2 = C::N2;
 #ifdef MMPC_T4_PROFILE
     long long t_st = clock64();
@@ -84,33 +134,40 @@ __device__ __noinline__ void t4_forward(const T3Ctx<M, C::I, C::MODE>& cin, doub
     const bool worker = C::is_worker(tid);
     const int w = C::widx(tid), wi = w % I, wj = C::slot_of(w / I);
     double* red = smem + C::SM_RED;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + C::SM_BAR);  // [0,1] chain, [2,3] post
     const int nch = (N + C::CF - 1) / C::CF;
-    auto stage_chunk = [&](int ch) {
-        const int k0 = ch * C::CF, kn = min(C::CF, N - k0);
-        double* buf = smem + C::SM_REC + (ch & 1) * C::BUF;
-        for (int s = 0; s < kn; ++s) {
-            const double* fg = fg_tile + (size_t)(k0 + s) * C::FG * I;
-            const double* kg = kg_tile + (size_t)(k0 + s) * C::KG * I;
-            double* dst = buf + (size_t)s * C::RS * I;
-            for (int e = w * 2; e < C::RS_F * I; e += C::WORKERS * 2) cp_async16(dst + e, fg + e);
-            for (int e = w * 2; e < C::KG * I; e += C::WORKERS * 2) cp_async16(dst + C::RS_K * I + e, kg + e);
+    constexpr unsigned B_CHAIN = C::REC_C * I * 8, B_POST = C::REC_P * I * 8;
+    const double* rec_tile = fg_tile;  // FG | KG | PG are ONE record per node here (kg_tile, pg_tile point into it)
+    (void)kg_tile; (void)pg_tile;
+    // bulk copies of step ch: the chain parts of chunk ch+1 and the post parts of chunk ch, one copy per worker thread w < 2 CF
+    // (a single thread needs ~90 cycles per copy to issue them); worker 0 announces the bytes.  A copy may complete before the
+    // announcement: the phase cannot end before the announcing thread's arrival.
+    auto issue_loads = [&](int ch_chain, int ch_post) {
+        const int knc = ch_chain < nch ? min(C::CF, N - ch_chain * C::CF) : 0, knp = ch_post >= 0 ? min(C::CF, N - ch_post * C::CF) : 0;
+        if (w == 0) {
+            if (knc) t4_mbar_arrive_expect_tx(&bars[ch_chain & 1], (unsigned)knc * B_CHAIN);
+            if (knp) t4_mbar_arrive_expect_tx(&bars[2 + (ch_post & 1)], (unsigned)knp * B_POST);
+        }
+        if (w < knc) {
+            const int k = ch_chain * C::CF + w;
+            t4_bulk_load(smem + C::SM_REC + (ch_chain & 1) * C::BUF + C::FW_CHAIN + (size_t)w * C::RC * I, rec_tile + (size_t)k * C::REC * I, B_CHAIN, &bars[ch_chain & 1]);
+        } else if (w >= C::CF && w - C::CF < knp) {
+            const int s = w - C::CF, k = ch_post * C::CF + s;
+            t4_bulk_load(smem + C::SM_REC + (ch_post & 1) * C::BUF + C::FW_POST + (size_t)s * C::RP * I, rec_tile + ((size_t)k * C::REC + C::REC_C) * I, B_POST,
+                         &bars[2 + (ch_post & 1)]);
         }
     };
     // does this thread's instance still iterate?  (instances that do not: their multipliers are handed over unchanged)
     const bool act = smem[C::SM_INST + 2 * I + (worker ? wi : (tid < I ? tid : 0))] != 0.0;
     double gsum = 0.0, lmax = 0.0;
     bool fin = true;
-    // worker (i, node k): everything that depends on dz_k, dz_{k+1} but is not on the roll-out's dependent chain
-    auto post_node = [&](int k) {
-        const double* d = c.DV + (size_t)k * S * I;
-        const double* fq = fg_tile + ((size_t)k * C::FG + C::FG_Q) * I + wi;
-        const double* pg = pg_tile + (size_t)k * C::PG * I + wi;
-        double dx[NX], dv[NU], du[NU], dxn[NX], q[N2], Pr[C::PG], zu[NU], zx[NX], lk[NX];
-        MMPC_UNROLL for (int a = 0; a < NX; ++a) { dx[a] = d[a * I]; dxn[a] = d[(S + a) * I]; }
-        MMPC_UNROLL for (int a = 0; a < NU; ++a) { du[a] = d[(NX + a) * I]; dv[a] = k ? d[(NX + a - S) * I] : 0.0; }
-        MMPC_UNROLL for (int a = 0; a < N2; ++a) q[a] = fq[a * I];
-        MMPC_UNROLL for (int a = 0; a < C::PG; ++a) Pr[a] = pg[a * I];
+    // worker (i, node k = k0 + s of chunk ch): everything that depends on dz_k, dz_{k+1} but is not on the roll-out's chain
+    auto post_node = [&](int ch, int s) {
+        const int k = ch * C::CF + s;
+        const double* pb = smem + C::SM_REC + (ch & 1) * C::BUF + C::FW_POST + (size_t)s * C::RP * I + wi;
+        const double* dzb = smem + C::SM_REC + (ch & 1) * C::BUF + C::FW_DZ + (size_t)s * S * I + wi;  // slot s: (dv, dx); slot s+1: (du, dx+)
         double* z = c.V + (size_t)k * S * I;
+        double zu[NU], zx[NX], lk[NX];
         MMPC_UNROLL for (int a = 0; a < NU; ++a) zu[a] = 0.0;
         MMPC_UNROLL for (int a = 0; a < NX; ++a) zx[a] = lk[a] = 0.0;
         if (act) {
@@ -119,17 +176,20 @@ __device__ __noinline__ void t4_forward(const T3Ctx<M, C::I, C::MODE>& cin, doub
         } else {
             MMPC_UNROLL for (int a = 0; a < NX; ++a) lk[a] = c.LAM[((size_t)k * NX + a) * I];
         }
+        double dx[NX], dv[NU], du[NU], dxn[NX];
+        MMPC_UNROLL for (int a = 0; a < NU; ++a) { dv[a] = dzb[a * I]; du[a] = dzb[(S + a) * I]; }
+        MMPC_UNROLL for (int a = 0; a < NX; ++a) { dx[a] = dzb[(NU + a) * I]; dxn[a] = dzb[(S + NU + a) * I]; }
         // directional derivative of the objective: q~ . (dx, dv, du)
-        MMPC_UNROLL for (int a = 0; a < NX; ++a) gsum = fma(q[a], dx[a], gsum);
+        MMPC_UNROLL for (int a = 0; a < NX; ++a) gsum = fma(pb[(C::RP_Q + a) * I], dx[a], gsum);
         MMPC_UNROLL for (int a = 0; a < NU; ++a) {
-            gsum = fma(q[NX + a], dv[a], gsum);
-            gsum = fma(q[S + a], du[a], gsum);
+            gsum = fma(pb[(C::RP_Q + NX + a) * I], dv[a], gsum);
+            gsum = fma(pb[(C::RP_Q + S + a) * I], du[a], gsum);
         }
         // lam_k+ = (P_{k+1} (dx_{k+1}, du_k) + p_{k+1})_x
         MMPC_UNROLL for (int a = 0; a < NX; ++a) {
-            double t = Pr[C::PG_X + a];
-            MMPC_UNROLL for (int b = 0; b < NX; ++b) t = fma(Pr[C::PG_XX + trisym(a, b, NX)], dxn[b], t);
-            MMPC_UNROLL for (int b = 0; b < NU; ++b) t = fma(Pr[C::PG_XV + a * NU + b], du[b], t);
+            double t = pb[(C::RP_P + C::PG_X + a) * I];
+            MMPC_UNROLL for (int b = 0; b < NX; ++b) t = fma(pb[(C::RP_P + C::PG_XX + trisym(a, b, NX)) * I], dxn[b], t);
+            MMPC_UNROLL for (int b = 0; b < NU; ++b) t = fma(pb[(C::RP_P + C::PG_XV + a * NU + b) * I], du[b], t);
             lmax = fmax(lmax, fabs(t));
             fin = fin && isfinite(t) && isfinite(dxn[a]);
             c.LAMN[((size_t)k * NX + a) * I] = act ? t : lk[a];
@@ -137,63 +197,57 @@ __device__ __noinline__ void t4_forward(const T3Ctx<M, C::I, C::MODE>& cin, doub
         if (act) {  // the full step, applied at once (its Armijo test follows the next sweep)
             MMPC_UNROLL for (int a = 0; a < NU; ++a) z[(NX + a) * I] = zu[a] + du[a];
             MMPC_UNROLL for (int a = 0; a < NX; ++a) z[(S + a) * I] = zx[a] + dxn[a];
+            // global copy of the step: only the (rare) backtracking of t4_armijo reads it
+            MMPC_UNROLL for (int a = 0; a < NU; ++a) c.DV[((size_t)k * S + NX + a) * I] = du[a];
+            MMPC_UNROLL for (int a = 0; a < NX; ++a) c.DV[((size_t)(k + 1) * S + a) * I] = dxn[a];
         }
 #ifndef MMPC_T4_NO_DISCARD
-        // The node's record (FG | KG | PG rows of this tile) is dead now -- the roll-out consumed its staged copy a step ago, the
-        // values above are in registers -- and the next backward sweep overwrites every byte of it.  Tell L2 so: the lines are
-        // dropped instead of being written back to HBM when they are evicted (the record stream was ~1 GB of DRAM traffic per
-        // launch, profiles/r1_bench_solve_t3_ncu_full.txt).  Whole 128-byte lines only: rows of 32 instances.
+        // The node's record (FG | KG | PG rows of this tile) is dead now -- its bulk copies completed before this step -- and
+        // the next backward sweep overwrites every byte of it.  Tell L2 so: the lines are dropped instead of being written back
+        // to HBM when they are evicted (the record stream was ~1 GB of DRAM traffic per launch,
+        // profiles/r1_bench_solve_t3_ncu_full.txt).  Whole 128-byte lines only: rows of 32 instances.
         if constexpr (I == 32) {
-            __syncwarp();  // every lane of the node's warp has its values
-            const char* fgb = reinterpret_cast<const char*>(fg_tile + (size_t)k * C::FG * I);
-            const char* kgb = reinterpret_cast<const char*>(kg_tile + (size_t)k * C::KG * I);
-            const char* pgb = reinterpret_cast<const char*>(pg_tile + (size_t)k * C::PG * I);
-            MMPC_UNROLL for (int l = 0; l < 2 * C::FG; l += 32) if (l + wi < 2 * C::FG) t4_discard_l2(fgb + (size_t)(l + wi) * 128);
-            MMPC_UNROLL for (int l = 0; l < 2 * C::KG; l += 32) if (l + wi < 2 * C::KG) t4_discard_l2(kgb + (size_t)(l + wi) * 128);
-            MMPC_UNROLL for (int l = 0; l < 2 * C::PG; l += 32) if (l + wi < 2 * C::PG) t4_discard_l2(pgb + (size_t)(l + wi) * 128);
+            const char* recb = reinterpret_cast<const char*>(rec_tile + (size_t)k * C::REC * I);
+            MMPC_UNROLL for (int l = 0; l < 2 * C::REC; l += 32) if (l + wi < 2 * C::REC) t4_discard_l2(recb + (size_t)(l + wi) * 128);
         }
 #endif
     };
     auto post_chunk = [&](int ch) {
-        const int k0 = ch * C::CF, kn = min(C::CF, N - k0);
-        if (wj < kn) post_node(k0 + wj);
-    };
-    // what post_node reads besides dz (value-function rows, q~, the iterate / multipliers it updates) does not depend on the
-    // roll-out: L2 -> L1 one step ahead, so that the post-processing of a chunk is one short round trip
-    auto prefetch_chunk = [&](int ch) {
-        const int k0 = ch * C::CF, kn = min(C::CF, N - k0);
-        if (wj >= kn) return;
-        const int k = k0 + wj;
-        const double* fq = fg_tile + ((size_t)k * C::FG + C::FG_Q) * I + wi;
-        const double* pg = pg_tile + (size_t)k * C::PG * I + wi;
-        MMPC_UNROLL for (int a = 0; a < N2; ++a) t3_prefetch(fq + a * I);
-        MMPC_UNROLL for (int a = 0; a < C::PG; ++a) t3_prefetch(pg + a * I);
-        if (act) { MMPC_UNROLL for (int a = 0; a < S; ++a) t3_prefetch(c.V + ((size_t)k * S + NX + a) * I); }
-        else { MMPC_UNROLL for (int a = 0; a < NX; ++a) t3_prefetch(c.LAM + ((size_t)k * NX + a) * I); }
+        const int kn = min(C::CF, N - ch * C::CF);
+        t4_mbar_wait(&bars[2 + (ch & 1)], (phase[2 + (ch & 1)] + (unsigned)(ch >> 1)) & 1u);
+        if (wj < kn) post_node(ch, wj);
     };
 #ifdef MMPC_T4_PROFILE
-    long long t_work = 0, t_all0 = clock64();
+    long long t_work = 0;
 #endif
-    if (worker) {
-        stage_chunk(0);
-        prefetch_chunk(0);
-        cp_async_wait_all();
-    }
+    // the record buffers were last touched by the backward sweep's st.shared / ld.shared and the node records were written
+    // with st.global: order all of it before the bulk copies
+    t4_fence_proxy_async();
     __syncwarp();
     __syncthreads();
-    T4_STAMP(1, t_st);  // first chunk staged
+    if (worker) issue_loads(0, -1);
+    T4_STAMP(1, t_st);
     if (worker) {
         for (int ch = 0; ch < nch; ++ch) {
             const long long t0 = T4_CLK();
-            if (ch + 1 < nch) { stage_chunk(ch + 1); prefetch_chunk(ch + 1); }
+#ifdef MMPC_T4_PROFILE
+            long long tw = t0;
+#endif
+            issue_loads(ch + 1, ch);
+            if (act && ch > 0 && wj < min(C::CF, N - (ch - 1) * C::CF)) {  // the iterate rows post_node updates -> L1
+                const int k = (ch - 1) * C::CF + wj;
+                MMPC_UNROLL for (int a = 0; a < S; ++a) t3_prefetch(c.V + ((size_t)k * S + NX + a) * I);
+            }
+            T4_STAMPW(6, tw);
             if (ch > 0) post_chunk(ch - 1);
-            cp_async_wait_all();
+            T4_STAMPW(7, tw);
 #ifdef MMPC_T4_PROFILE
             t_work += T4_CLK() - t0;
 #else
             (void)t0;
 #endif
-            t3_cta_barrier();  // the step of chunk ch is visible to the workers; buffer (ch+1)&1 is staged
+            t3_cta_barrier();  // dz of chunk ch is in shared memory; the buffers of parity (ch+1)&1 are free again
+            T4_STAMPW(9, tw);
         }
         post_chunk(nch - 1);
         red[(0 * C::CB + wj) * I + wi] = gsum;
@@ -205,22 +259,29 @@ __device__ __noinline__ void t4_forward(const T3Ctx<M, C::I, C::MODE>& cin, doub
         MMPC_UNROLL for (int a = 0; a < NU; ++a) dv[a] = 0.0;
         for (int ch = 0; ch < nch; ++ch) {
             const long long t0 = T4_CLK();
+#ifdef MMPC_T4_PROFILE
+            long long ts = t0;
+#endif
             if (tid < I) {
                 const int k0 = ch * C::CF, kn = min(C::CF, N - k0);
-                const double* rec = smem + C::SM_REC + (ch & 1) * C::BUF;
-                for (int s = 0; s < kn; ++s) {
-                    const int k = k0 + s;
-                    const double* const recp = rec + (size_t)s * C::RS * I + tid;
+                const double* __restrict__ rec = smem + C::SM_REC + (ch & 1) * C::BUF + C::FW_CHAIN;
+                double* __restrict__ dzb = smem + C::SM_REC + (ch & 1) * C::BUF + C::FW_DZ + tid;
+                MMPC_UNROLL for (int a = 0; a < NU; ++a) dzb[a * I] = dv[a];
+                MMPC_UNROLL for (int a = 0; a < NX; ++a) dzb[(NU + a) * I] = dx[a];
+                t4_mbar_wait(&bars[ch & 1], (phase[ch & 1] + (unsigned)(ch >> 1)) & 1u);
+                T4_STAMP(12, ts);
+                MMPC_UNROLL for (int s = 0; s < C::CF; ++s) if (s < kn) {
+                    const double* __restrict__ const recp = rec + (size_t)s * C::RC * I + tid;
 #define T4_F(f) recp[(f) * I]
                     // short accumulation trees: the stage's dependent chain is du (2 fma + 2 add after dx) -> dx+ (<= NU fma)
                     double du[NU], dxn[NX];
                     MMPC_UNROLL for (int a = 0; a < NU; ++a) {
-                        double ta = T4_F(C::RS_K + C::KG_K0 + a), tb = 0.0, tc = 0.0;
+                        double ta = T4_F(C::RC_K + C::KG_K0 + a), tb = 0.0, tc = 0.0;
                         MMPC_UNROLL for (int q = 0; q < NX; ++q) {
-                            if (q < (NX + 1) / 2) ta = fma(T4_F(C::RS_K + C::KG_KX + a * NX + q), dx[q], ta);
-                            else tb = fma(T4_F(C::RS_K + C::KG_KX + a * NX + q), dx[q], tb);
+                            if (q < (NX + 1) / 2) ta = fma(T4_F(C::RC_K + C::KG_KX + a * NX + q), dx[q], ta);
+                            else tb = fma(T4_F(C::RC_K + C::KG_KX + a * NX + q), dx[q], tb);
                         }
-                        MMPC_UNROLL for (int q = 0; q < NU; ++q) tc = fma(T4_F(C::RS_K + C::KG_KV + a * NU + q), dv[q], tc);
+                        MMPC_UNROLL for (int q = 0; q < NU; ++q) tc = fma(T4_F(C::RC_K + C::KG_KV + a * NU + q), dv[q], tc);
                         du[a] = (ta + tb) + tc;
                     }
                     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
@@ -230,24 +291,26 @@ __device__ __noinline__ void t4_forward(const T3Ctx<M, C::I, C::MODE>& cin, doub
                         dxn[a] = t;
                     }
 #undef T4_F
-                    MMPC_UNROLL for (int a = 0; a < NU; ++a) c.DV[((size_t)k * S + NX + a) * I] = du[a];
-                    MMPC_UNROLL for (int a = 0; a < NX; ++a) c.DV[((size_t)(k + 1) * S + a) * I] = dxn[a];
+                    double* const dzs = dzb + (size_t)(s + 1) * S * I;
+                    MMPC_UNROLL for (int a = 0; a < NU; ++a) dzs[a * I] = du[a];
+                    MMPC_UNROLL for (int a = 0; a < NX; ++a) dzs[(NU + a) * I] = dxn[a];
                     MMPC_UNROLL for (int a = 0; a < NX; ++a) dx[a] = dxn[a];
                     MMPC_UNROLL for (int a = 0; a < NU; ++a) dv[a] = du[a];
                 }
             }
 #ifdef MMPC_T4_PROFILE
             t_work += T4_CLK() - t0;
+            T4_STAMP(10, ts);
 #else
             (void)t0;
 #endif
             t3_cta_barrier();
+            T4_STAMP(11, ts);
         }
     }
-#if defined(MMPC_T4_PROFILE) && defined(MMPC_T3_PROFILE_SWEEPS)
-    if (blockIdx.x == 0 && (tid == 0 || tid == 32))
-        printf("[t4 forward ] tid %d busy %lld of %lld cycles (%d chunks of %d)\n", tid, t_work, clock64() - t_all0, nch, C::CF);
-#endif
+    // every barrier has completed ceil((nch - parity) / 2) more phases
+    phase[0] += (unsigned)((nch + 1) >> 1); phase[1] += (unsigned)(nch >> 1);
+    phase[2] += (unsigned)((nch + 1) >> 1); phase[3] += (unsigned)(nch >> 1);
     T4_STAMP(2, t_st);  // pipeline loop
     __syncwarp();
     __syncthreads();
@@ -265,6 +328,7 @@ __device__ __noinline__ void t4_forward(const T3Ctx<M, C::I, C::MODE>& cin, doub
     T4_STAMP(4, t_st);  // reduction
 #ifdef MMPC_T4_PROFILE
     if (blockIdx.x == 0 && tid == 0) t4_dbg[14] = clock64();
+    (void)t_work;
 #endif
 }
 
@@ -317,6 +381,13 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
 #endif
     const int tid = threadIdx.x, tile = io.b0 / C::I + blockIdx.x;  // b0 is a multiple of the tile width (the ABI layer cuts sub-batches on tile boundaries)
     const bool worker = C::is_worker(tid);
+    // mbarriers of the forward sweep's bulk copies: initialised once, `fwd_phase` counts their completed phases
+    if (tid == 0) {
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + C::SM_BAR);
+        for (int q = 0; q < 4; ++q) t4_mbar_init(&bars[q], 1u);
+        t4_fence_barrier_init();
+    }
+    unsigned fwd_phase[4] = {0u, 0u, 0u, 0u};
     // a thread's instance: serial lane tid -> instance tid; worker w -> instance w % I (node slot w / I)
     const int i = worker ? C::widx(tid) % I : (tid < I ? tid : 0);
     const int j = worker ? C::slot_of(C::widx(tid) / I) : 0;
@@ -333,9 +404,10 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
     c.DV = W.DV2 + (size_t)tile * I * NV + i; c.LAMN = W.LAMN2 + (size_t)tile * I * Mc + i;
     c.LINp = W.LIN2 + (size_t)b * C::LIN;
     c.traj = io.traj + (size_t)bi * N * NX;
-    double* fg_tile = W.FG2 + (size_t)tile * I * N * C::FG;
-    double* kg_tile = W.KG2 + (size_t)tile * I * N * C::KG;
-    double* pg_tile = W.PG2 + (size_t)tile * I * N * C::PG;
+    // node records of the tile: FG2, KG2, PG2 are one contiguous region of the arena (mmpc_api.cu), used here as [node][REC rows][I]
+    double* fg_tile = W.FG2 + (size_t)tile * I * N * C::REC;
+    double* kg_tile = fg_tile + (size_t)C::REC_K * I;
+    double* pg_tile = fg_tile + (size_t)C::REC_PG * I;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) c.Q[a] = W.Qw[(size_t)a * W.Bp + bi];
     MMPC_UNROLL for (int a = 0; a < NU; ++a) {
         c.R[a] = W.Rw[(size_t)a * W.Bp + bi];
@@ -453,7 +525,7 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
 #ifdef MMPC_T4_PROFILE
         if (blockIdx.x == 0 && tid == 0) t4_dbg[15] = tf0;
 #endif
-        t4_forward<M, C>(c, smem, tid, fo, fg_tile, kg_tile, pg_tile);
+        t4_forward<M, C>(c, smem, tid, fo, fg_tile, kg_tile, pg_tile, fwd_phase);
         const long long tf1 = T4_CLK();
 #ifdef MMPC_T4_PROFILE
         if (blockIdx.x == 0 && tid == 0) t4_dbg[5] += tf1 - t4_dbg[14];  // last statement -> back in the caller
@@ -521,6 +593,7 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
 #endif
     if (blockIdx.x == 0 && tid == 0) {
         printf("[t4 forward, all sweeps] call %lld  first chunk %lld  loop %lld  last post %lld  reduce %lld  return %lld\n", t4_dbg[0], t4_dbg[1], t4_dbg[2], t4_dbg[3], t4_dbg[4], t4_dbg[5]);
+        printf("[t4 forward loop, all sweeps] worker: issue %lld  post (incl. wait for its bulk copies) %lld  barrier %lld | serial: wait for bulk copies %lld  chain %lld  barrier %lld\n", t4_dbg[6], t4_dbg[7], t4_dbg[9], t4_dbg[12], t4_dbg[10], t4_dbg[11]);
         for (int q = 0; q < 16; ++q) t4_dbg[q] = 0;
     }
     if (blockIdx.x == 0 && tid == 0)
@@ -560,12 +633,12 @@ struct LaunchT4 {
             const int I = mmpc_t4_tile_width(W.B, io.variant >> 8);
             if (P.integrator == MMPC_RK4 && !P.is_linear) {
                 if (I == 8) return go<8, 4, 4, 1>(P, W, io, st);
-                if (I == 28) return go<28, 8, 8, 1>(P, W, io, st);
-                return go<32, 7, 7, 1>(P, W, io, st);
+                if (I == 28) return go<28, 8, 5, 1>(P, W, io, st);
+                return go<32, 7, 5, 1>(P, W, io, st);
             }
             if (I == 8) return go<8, 4, 4>(P, W, io, st);
-            if (I == 28) return go<28, 8, 8>(P, W, io, st);
-            return go<32, 7, 7>(P, W, io, st);
+            if (I == 28) return go<28, 8, 6>(P, W, io, st);
+            return go<32, 7, 5>(P, W, io, st);
         } else {
             return cudaErrorNotSupported;
         }
