@@ -45,6 +45,10 @@ typedef enum mmpc_mem { MMPC_MEM_HOST = 0, MMPC_MEM_DEVICE = 1 } mmpc_mem;
 /* integrator of the one-step map F: EULER is what the library's NLP uses
  * (ModelGenerator.cpp:33-34); RK4 (x `substeps`) is the MATLAB prototypes' (workingMPC_8_30_21.m:46-59). */
 typedef enum mmpc_integrator { MMPC_EULER = 0, MMPC_RK4 = 1 } mmpc_integrator;
+/* Lagrangian Hessian of the NLP under RK4 shooting: EXACT differentiates twice through the integrator (what CasADi's AD hands
+ * IPOPT in the prototypes, workingMPC_8_30_21.m:46-59,109-112; up to 4 sub-steps); GAUSS_NEWTON keeps the objective's
+ * first-order part only (same KKT point, linear convergence).  Euler / linearised shooting is always exact. */
+typedef enum mmpc_hessian { MMPC_HESSIAN_EXACT = 0, MMPC_HESSIAN_GAUSS_NEWTON = 1 } mmpc_hessian;
 
 /* per-instance solve status (the reference never inspects IPOPT's, ModelControl.cpp:159-160) */
 typedef enum mmpc_solve_status {
@@ -84,10 +88,12 @@ typedef struct mmpc_options {
     int warm_start;        /* 1: start from the previous solution of the same instance slot
                                  (ModelControl.cpp:161: args["x0"] = result), 0: always cold (zeros) */
     int warm_start_duals;  /* 0: reference behaviour (primal only); 1: also reuse lam_g */
-    int kernel_variant;    /* 0 = auto: T3 for nx+2nu <= 8, else T2; T1 for what those do not implement.
-                              1 / 2 / 3 request T1 / T2 / T3; 3 + 256*k forces T3's tile configuration k (1 = 8x4x4,
-                              2 = 32x7x5) -- experiments and tests only.  Changing it forgets the warm start. */
-    int reserved[8];
+    int kernel_variant;    /* 0 = auto: T4 for nx+2nu <= 8 without finite bounds, T3 with them, else T2; T1 for what
+                              those do not implement.  1 / 2 / 3 / 4 request T1 / T2 / T3 / T4; 3 + 256*k and 4 + 256*k force a
+                              tile configuration (mmpc_solve_t3.cuh, mmpc_solve_t4.cuh) -- experiments and tests only.
+                              Changing it forgets the warm start. */
+    int hessian;           /* MMPC_HESSIAN_EXACT (default) / MMPC_HESSIAN_GAUSS_NEWTON: RK4 shooting only */
+    int reserved[7];
 } mmpc_options;
 
 /* Per-instance statistics returned by mmpc_solve (40 bytes). */

@@ -157,6 +157,100 @@ __device__ void step_rk4(double h, int substeps, const double* x, const double* 
     }
 }
 
+// RK4 x `substeps` with EXACT second derivatives: Hs = sum_i wbar_i d2F_i/dz2 (packed upper triangle over z = (x, u)), where
+// wbar_i = wq_i (F_i - r_i) + lam_i are the NLP's weights of nlp_hess_l (wq == nullptr: wbar = lam, a plain contraction).
+// The interval map is a composition of 4 * substeps evaluations of f joined by linear operations, so
+//     d2(wbar' F)/dz2 = sum over evaluations e of  W_e' [ sum_i kbar_{e,i} d2f_i/d(x,u)2 at the stage point ] W_e,
+// with W_e = d(stage point, u)/dz (forward sensitivities) and kbar_e the adjoint of the evaluation's output (reverse sweep
+// through the Butcher tableau: kbar_4 = hs b_4 v, xbar_4 = A_4' kbar_4, kbar_3 = hs b_3 v + hs xbar_4, ...,
+// v_prev = v + sum_j xbar_j).  Pass 1 (forward) stores the stage points and their sensitivities in local memory; pass 2
+// (reverse) calls the model's fABH at every stage point with weights kbar (it returns A for the adjoint and the contraction).
+// This is the Hessian CasADi's AD gives IPOPT for the prototypes' NLP (workingMPC_8_30_21.m:46-59,109-112: RK4 x 4 inside
+// opti.subject_to(x(:,k+1)==F(x(:,k),u(:,k)))).  substeps <= MMPC_RK4_HESS_MAX_SUBSTEPS.
+#define MMPC_RK4_HESS_MAX_SUBSTEPS 4
+template <class M>
+__device__ void step_rk4_hess(double h, int substeps, const double* x, const double* u, const double* wq, const double* r, const double* lam,
+                              double* F, double* Fx, double* Fu, double* Hs) {
+    constexpr int NX = M::NX, NU = M::NU, S = NX + NU, NH = S * (S + 1) / 2, MAXE = 4 * MMPC_RK4_HESS_MAX_SUBSTEPS;
+    const double hs = h / (double)substeps;
+    double xst[MAXE][NX], Tst[MAXE][NX * S];  // stage points and d(stage point)/dz, z = (x, u)
+    double xs[NX], Sz[NX * S];
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) xs[i] = x[i];
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) MMPC_UNROLL for (int j = 0; j < S; ++j) Sz[i * S + j] = (i == j) ? 1.0 : 0.0;
+    for (int m = 0; m < substeps; ++m) {
+        double xa[NX], acc[NX], accz[NX * S], Tz[NX * S];
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) { xa[i] = xs[i]; acc[i] = 0.0; }
+        MMPC_UNROLL for (int i = 0; i < NX * S; ++i) { Tz[i] = Sz[i]; accz[i] = 0.0; }
+#pragma unroll 1
+        for (int st = 0; st < 4; ++st) {
+            const double wgt = (st == 0 || st == 3) ? 1.0 / 6.0 : 1.0 / 3.0;
+            const double adv = (st == 2) ? 1.0 : 0.5;
+            const int e = 4 * m + st;
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) xst[e][i] = xa[i];
+            MMPC_UNROLL for (int i = 0; i < NX * S; ++i) Tst[e][i] = Tz[i];
+            double k[NX], A[NX * NX], B[NX * NU], kz[NX * S];
+            M::fAB(xa, u, k, A, B);
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) MMPC_UNROLL for (int j = 0; j < S; ++j) {
+                double t = j >= NX ? B[i * NU + j - NX] : 0.0;
+                MMPC_UNROLL for (int l = 0; l < NX; ++l) t = fma(A[i * NX + l], Tz[l * S + j], t);
+                kz[i * S + j] = t;
+            }
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+                acc[i] = fma(wgt, k[i], acc[i]);
+                xa[i] = fma(adv * hs, k[i], xs[i]);
+            }
+            MMPC_UNROLL for (int i = 0; i < NX * S; ++i) { accz[i] = fma(wgt, kz[i], accz[i]); Tz[i] = fma(adv * hs, kz[i], Sz[i]); }
+        }
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) xs[i] = fma(hs, acc[i], xs[i]);
+        MMPC_UNROLL for (int i = 0; i < NX * S; ++i) Sz[i] = fma(hs, accz[i], Sz[i]);
+    }
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+        F[i] = xs[i];
+        MMPC_UNROLL for (int j = 0; j < NX; ++j) Fx[i * NX + j] = Sz[i * S + j];
+        MMPC_UNROLL for (int j = 0; j < NU; ++j) Fu[i * NU + j] = Sz[i * S + NX + j];
+    }
+    // ---- reverse sweep ----
+    double v[NX], zero[NX];
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) { v[i] = (wq ? wq[i] * (xs[i] - r[i]) : 0.0) + lam[i]; zero[i] = 0.0; }
+    MMPC_UNROLL for (int i = 0; i < NH; ++i) Hs[i] = 0.0;
+    for (int m = substeps - 1; m >= 0; --m) {
+        double xsum[NX], xbar_next[NX];  // sum of the stage-point adjoints; adjoint of the NEXT stage point (feeds this stage's k)
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) { xsum[i] = 0.0; xbar_next[i] = 0.0; }
+#pragma unroll 1
+        for (int st = 3; st >= 0; --st) {
+            const double wgt = (st == 0 || st == 3) ? 1.0 / 6.0 : 1.0 / 3.0;
+            const double adv_next = (st == 3) ? 0.0 : ((st == 2) ? 1.0 : 0.5);  // stage st+1's point = xs + adv_next hs k_st
+            const int e = 4 * m + st;
+            double kbar[NX];
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) kbar[i] = hs * fma(wgt, v[i], adv_next * xbar_next[i]);
+            double kk[NX], A[NX * NX], B[NX * NU], Hl[NH], xa[NX], T[NX * S];
+            MMPC_UNROLL for (int i = 0; i < NX; ++i) xa[i] = xst[e][i];
+            MMPC_UNROLL for (int i = 0; i < NX * S; ++i) T[i] = Tst[e][i];
+            M::fABH(xa, u, zero, kbar, kk, A, B, Hl);
+            // Hs += W' Hl W,  W = [T; (0 I)]  (S x S): first Y = Hl W (rows p of the symmetric Hl), then W' Y, upper triangle
+            double Y[S * S];
+            MMPC_UNROLL for (int p = 0; p < S; ++p) MMPC_UNROLL for (int j = 0; j < S; ++j) {
+                double t = (j >= NX) ? Hl[trisym(p, j, S)] : 0.0;  // u rows of W are (0 I)
+                MMPC_UNROLL for (int l = 0; l < NX; ++l) t = fma(Hl[trisym(p, l, S)], T[l * S + j], t);
+                Y[p * S + j] = t;
+            }
+            MMPC_UNROLL for (int a = 0; a < S; ++a) MMPC_UNROLL for (int j = a; j < S; ++j) {
+                double t = (a >= NX) ? Y[a * S + j] : 0.0;
+                MMPC_UNROLL for (int l = 0; l < NX; ++l) t = fma(T[l * S + a], Y[l * S + j], t);
+                Hs[tri(a, j, S)] += t;
+            }
+            // adjoint of this stage's point: A' kbar
+            MMPC_UNROLL for (int j = 0; j < NX; ++j) {
+                double t = 0.0;
+                MMPC_UNROLL for (int i = 0; i < NX; ++i) t = fma(A[i * NX + j], kbar[i], t);
+                xbar_next[j] = t;
+                xsum[j] += t;
+            }
+        }
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) v[i] += xsum[i];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // eval_nodes: n independent shooting nodes, SoA in / SoA out, one thread per node (HBM-bound stream)
 // ---------------------------------------------------------------------------------------------
@@ -177,7 +271,8 @@ __global__ void __launch_bounds__(128) eval_nodes_kernel(double h, int rk4_subst
                 wr[i] = w[i * n + j];
                 zero[i] = 0.0;
             }
-            step_euler<M, 2>(h, xr, ur, zero, zero, wr, F, fx, fu, hs);
+            if (RK4) step_rk4_hess<M>(h, rk4_substeps, xr, ur, nullptr, nullptr, wr, F, fx, fu, hs);  // exact, through the integrator
+            else step_euler<M, 2>(h, xr, ur, zero, zero, wr, F, fx, fu, hs);
             MMPC_UNROLL for (int i = 0; i < NH; ++i) __stcs(&H[i * n + j], hs[i]);
         } else if (RK4) {  // separate instantiation: keeps the Euler streaming kernel at its low register count
             step_rk4<M, 1>(h, rk4_substeps, xr, ur, F, fx, fu);
@@ -285,8 +380,12 @@ __global__ void __launch_bounds__(128) nlp_eval_kernel(mmpc_problem P, int B, co
         }
         step_linear<M, 2>(P.h, x, u, A, Bm, pv.xdot_init, pv.x_init, pv.u_init, F, fx, fu, hs);
     } else if (P.integrator == MMPC_RK4) {
-        step_rk4<M, 1>(P.h, P.substeps, x, u, F, fx, fu);
-        MMPC_UNROLL for (int i = 0; i < NH; ++i) hs[i] = 0.0;  // Gauss-Newton part only (no d2F through the integrator)
+        if (Hzz && !P.gauss_newton) {
+            step_rk4_hess<M>(P.h, P.substeps, x, u, wq, r, lam, F, fx, fu, hs);
+        } else {
+            step_rk4<M, 1>(P.h, P.substeps, x, u, F, fx, fu);
+            MMPC_UNROLL for (int i = 0; i < NH; ++i) hs[i] = 0.0;  // Gauss-Newton part only
+        }
     } else {
         step_euler<M, 2>(P.h, x, u, wq, r, lam, F, fx, fu, hs);
     }
@@ -401,7 +500,8 @@ template <class M>
 struct Launch {
     static cudaError_t eval_nodes(const mmpc_problem& P, long long n, const double* x, const double* u, const double* xn,
                                   const double* w, double* g, double* Fx, double* Fu, double* H, cudaStream_t st, int* launches) {
-        if (P.is_linear || (P.integrator != MMPC_EULER && w)) return cudaErrorNotSupported;  // no second derivatives through RK4
+        if (P.is_linear) return cudaErrorNotSupported;
+        if (P.integrator == MMPC_RK4 && w && P.substeps > MMPC_RK4_HESS_MAX_SUBSTEPS) return cudaErrorNotSupported;
         if (n <= 0) return cudaSuccess;
         const int rk = P.integrator == MMPC_RK4 ? P.substeps : 0;
         int dev = 0, sms = 148;
@@ -409,7 +509,8 @@ struct Launch {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const long long want = (n + 127) / 128;
         const int grid = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);  // grid-stride, multiple of the SM count
-        if (w) eval_nodes_kernel<M, true, false><<<grid, 128, 0, st>>>(P.h, 0, n, x, u, xn, w, g, Fx, Fu, H);
+        if (w && rk) eval_nodes_kernel<M, true, true><<<grid, 128, 0, st>>>(P.h, rk, n, x, u, xn, w, g, Fx, Fu, H);
+        else if (w) eval_nodes_kernel<M, true, false><<<grid, 128, 0, st>>>(P.h, 0, n, x, u, xn, w, g, Fx, Fu, H);
         else if (rk) eval_nodes_kernel<M, false, true><<<grid, 128, 0, st>>>(P.h, rk, n, x, u, xn, w, g, Fx, Fu, H);
         else eval_nodes_kernel<M, false, false><<<grid, 128, 0, st>>>(P.h, 0, n, x, u, xn, w, g, Fx, Fu, H);
         if (launches) ++*launches;

@@ -48,8 +48,12 @@ struct SolveCtx {
             }
             step_linear<M, WANT>(P.h, x, u, A, Bm, xd0, x0, uinit, F, Fx, Fu, Hs);
         } else if (P.integrator == MMPC_RK4) {
-            step_rk4<M, (WANT >= 1 ? 1 : 0)>(P.h, P.substeps, x, u, F, Fx, Fu);
-            if (WANT >= 2) MMPC_UNROLL for (int i = 0; i < NH; ++i) Hs[i] = 0.0;  // Gauss-Newton Hessian under RK4
+            if (WANT >= 2 && !P.gauss_newton) {
+                step_rk4_hess<M>(P.h, P.substeps, x, u, wq, r, lam, F, Fx, Fu, Hs);  // exact Newton through the integrator
+            } else {
+                step_rk4<M, (WANT >= 1 ? 1 : 0)>(P.h, P.substeps, x, u, F, Fx, Fu);
+                if (WANT >= 2) MMPC_UNROLL for (int i = 0; i < NH; ++i) Hs[i] = 0.0;  // Gauss-Newton Hessian on request
+            }
         } else {
             step_euler<M, WANT>(P.h, x, u, wq, r, lam, F, Fx, Fu, Hs);
         }

@@ -142,7 +142,7 @@ template <class M, int I_, int MODE_ = 0>
 struct T3Ctx : T3CtxBounds<M, ((MODE_ >> 1) & 1) != 0> {
     static constexpr int NX = M::NX, NU = M::NU, S = NX + NU, I = I_;
     double h;                     // step size; is_linear / substeps: copies of the problem constants the sweeps need
-    int is_linear, substeps;
+    int is_linear, substeps, gauss_newton;
     int N;
     double *V, *LAM, *DV, *LAMN;  // this thread's instance inside the tile arrays: element e lives at [e * I]
     double* LINp;                 // linearisation data of the instance (AoS)
@@ -156,8 +156,12 @@ struct T3Ctx : T3CtxBounds<M, ((MODE_ >> 1) & 1) != 0> {
             MMPC_UNROLL for (int i = 0; i < NX; ++i) x0[i] = V[(size_t)i * I];
             step_linear<M, WANT>(h, x, u, LINp, LINp + NX * NX, LINp + NX * NX + NX * NU, x0, uinit, F, Fx, Fu, Hs);
         } else if (MODE_ & 1) {
-            step_rk4<M, (WANT >= 1 ? 1 : 0)>(h, substeps, x, u, F, Fx, Fu);
-            if (WANT >= 2) MMPC_UNROLL for (int i = 0; i < S * (S + 1) / 2; ++i) Hs[i] = 0.0;  // Gauss-Newton Hessian under RK4
+            if (WANT >= 2 && !gauss_newton) {
+                step_rk4_hess<M>(h, substeps, x, u, wq, r, lam, F, Fx, Fu, Hs);  // exact Newton through the integrator
+            } else {
+                step_rk4<M, (WANT >= 1 ? 1 : 0)>(h, substeps, x, u, F, Fx, Fu);
+                if (WANT >= 2) MMPC_UNROLL for (int i = 0; i < S * (S + 1) / 2; ++i) Hs[i] = 0.0;  // Gauss-Newton Hessian on request
+            }
         } else {
             step_euler<M, WANT>(h, x, u, wq, r, lam, F, Fx, Fu, Hs);
         }
@@ -951,7 +955,7 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
 
     T3Ctx<M, I, C::MODE> c;
     c.N = N;
-    c.h = P.h; c.is_linear = P.is_linear; c.substeps = P.substeps;
+    c.h = P.h; c.is_linear = P.is_linear; c.substeps = P.substeps; c.gauss_newton = P.gauss_newton;
     // the iterate lives tile-wise, [element][instance]: every access of a warp is a run of full sectors whatever I is
     c.V = W.V2 + (size_t)tile * I * NV + i; c.LAM = W.LAM2 + (size_t)tile * I * Mc + i;
     c.DV = W.DV2 + (size_t)tile * I * NV + i; c.LAMN = W.LAMN2 + (size_t)tile * I * Mc + i;
@@ -1224,8 +1228,9 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
         //   linearised model: the problem is a QP, one full step solves it;
         //   RK4 (Gauss-Newton, linear rate): not predicted -- extrapolating the observed contraction was measured a loss at
         //   one sub-step (1.61 -> 1.71 ms) and a small gain at four (3.58 -> 3.44 ms).
-        if constexpr (C::BD == 0 && C::RK == 0) {
-            const bool expect = alpha == 1.0 && (P.is_linear || err <= T3_EXPECT_CONVERGED_BELOW);
+        if constexpr (C::BD == 0) {
+            const bool newton = C::RK == 0 || !P.gauss_newton;
+            const bool expect = newton && alpha == 1.0 && (P.is_linear || err <= T3_EXPECT_CONVERGED_BELOW);
             expect_converged = !__syncthreads_or(active && !expect);
         }
 #ifdef MMPC_T3_PROFILE

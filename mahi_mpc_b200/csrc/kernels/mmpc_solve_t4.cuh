@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
 
     T3Ctx<M, I, C::MODE> c;
     c.N = N;
-    c.h = P.h; c.is_linear = P.is_linear; c.substeps = P.substeps;
+    c.h = P.h; c.is_linear = P.is_linear; c.substeps = P.substeps; c.gauss_newton = P.gauss_newton;
     // the iterate lives tile-wise, [element][instance] (T3's layout)
     c.V = W.V2 + (size_t)tile * I * NV + i; c.LAM = W.LAM2 + (size_t)tile * I * Mc + i;
     c.DV = W.DV2 + (size_t)tile * I * NV + i; c.LAMN = W.LAMN2 + (size_t)tile * I * Mc + i;
@@ -543,11 +543,10 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
         { double* t = c.LAM; c.LAM = c.LAMN; c.LAMN = t; }  // LAMN holds lam+ (instances that iterate) or the old values (the others)
         ++it;
         // Is the next iterate expected to meet tol?  Then its test is done by the cheap residual sweep first (T3's rule).
-        if constexpr (C::RK == 0) {
-            const bool expect = P.is_linear || err <= T3_EXPECT_CONVERGED_BELOW;
+        {
+            const bool newton = C::RK == 0 || !P.gauss_newton;  // Gauss-Newton under RK4: linear rate, not predicted
+            const bool expect = newton && (P.is_linear || err <= T3_EXPECT_CONVERGED_BELOW);
             expect_converged = !__syncthreads_or(active && !expect);
-        } else {
-            if (!__syncthreads_or(active)) break;
         }
 #ifdef MMPC_T4_PROFILE
         tp_post += T4_CLK() - tf1;

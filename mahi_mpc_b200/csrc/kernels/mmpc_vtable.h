@@ -6,7 +6,7 @@
 
 #define MMPC_MAXNX 16
 #define MMPC_MAXNU 8
-#define MMPC_VTABLE_VERSION 6
+#define MMPC_VTABLE_VERSION 7
 
 struct mmpc_stats;  // public struct (include/mahi_mpc_b200.h)
 
@@ -18,6 +18,7 @@ struct mmpc_problem {
     int substeps;
     double h;        // step_size in seconds
     int bounded;     // any finite bound present
+    int gauss_newton;  // RK4 shooting only: drop the second derivatives of the integrator from the Lagrangian Hessian
     double x_min[MMPC_MAXNX], x_max[MMPC_MAXNX], u_min[MMPC_MAXNU], u_max[MMPC_MAXNU];
 };
 

@@ -195,25 +195,31 @@ def numeric(name: str):
     B = sp.lambdify(args, d["B"].tolist(), "numpy", cse=True)
     Hc = sp.lambdify(args + d["w"], d["Hc"].tolist(), "numpy", cse=True)
 
+    # complex arguments pass through (oracle/nlp.py differentiates the RK4 sensitivities by the complex-step method)
     def _arr(v, shape_like):
-        return np.array([[np.broadcast_to(np.asarray(e, dtype=np.float64), shape_like.shape)
+        dt = np.complex128 if np.iscomplexobj(shape_like) else np.float64
+        return np.array([[np.broadcast_to(np.asarray(e, dtype=dt), shape_like.shape)
                           for e in row] for row in v]) if isinstance(v[0], (list, tuple)) else \
-            np.array([np.broadcast_to(np.asarray(e, dtype=np.float64), shape_like.shape) for e in v])
+            np.array([np.broadcast_to(np.asarray(e, dtype=dt), shape_like.shape) for e in v])
+
+    def _in(*vs):
+        cplx = any(np.iscomplexobj(v) for v in vs)
+        return [np.asarray(v, np.complex128 if cplx else np.float64) for v in vs]
 
     def f_np(x, u):
-        x, u = np.asarray(x, float), np.asarray(u, float)
+        x, u = _in(x, u)
         return _arr(f(*x, *u), x[0])
 
     def A_np(x, u):
-        x, u = np.asarray(x, float), np.asarray(u, float)
+        x, u = _in(x, u)
         return _arr(A(*x, *u), x[0])
 
     def B_np(x, u):
-        x, u = np.asarray(x, float), np.asarray(u, float)
+        x, u = _in(x, u)
         return _arr(B(*x, *u), x[0])
 
     def Hc_np(x, u, w):
-        x, u, w = np.asarray(x, float), np.asarray(u, float), np.asarray(w, float)
+        x, u, w = _in(x, u, w)
         return _arr(Hc(*x, *u, *w), x[0])
 
     return dict(nx=mdl.nx, nu=mdl.nu, f=f_np, A=A_np, B=B_np, Hc=Hc_np)

@@ -38,6 +38,7 @@ class Problem:
     h: float = 0.002  # ex_model_generate.cpp:56
     is_linear: bool = False
     integrator: str = "euler"  # "euler" (library parity) | "rk4"
+    hessian: str = "exact"     # "exact" | "gauss_newton" (RK4 only: drop the integrator's second derivatives)
     substeps: int = 1
 
     def __post_init__(self):
@@ -161,11 +162,26 @@ class Problem:
         return x.T, Sx, Su
 
     def step_hess(self, X, U, P, W):
-        """sum_i W[k,i] grad^2_zz F_i for every node -> (N,s,s). Euler only (library parity)."""
-        if self.integrator != "euler":
-            raise NotImplementedError("exact second derivatives through RK4 are not restated")
-        f, A, B, Hc = self._ode(X.T, U.T, P, 2, W.T)
-        return self.h * np.moveaxis(Hc, 2, 0)
+        """sum_i W[k,i] grad^2_zz F_i for every node -> (N,s,s).
+        Euler: h times the model's Hessian contraction (library parity).  RK4 (workingMPC_8_30_21.m:46-59): the COMPLEX-STEP
+        derivative of the first-order sensitivities, H[:, j] = Im(Fz(z + i eps e_j)' w) / eps -- exact to rounding (no
+        subtraction), and a different route from the CUDA path's forward-over-adjoint sweep (mmpc_kernels.cuh: step_rk4_hess)."""
+        if self.integrator == "euler":
+            f, A, B, Hc = self._ode(X.T, U.T, P, 2, W.T)
+            return self.h * np.moveaxis(Hc, 2, 0)
+        if self.hessian == "gauss_newton":
+            return np.zeros((X.shape[0], self.s, self.s))
+        n, nx, s = X.shape[0], self.nx, self.s
+        eps = 1e-30
+        H = np.zeros((n, s, s))
+        Z = np.concatenate([X, U], axis=1).astype(complex)
+        for j in range(s):
+            Zp = Z.copy()
+            Zp[:, j] += 1j * eps
+            _, Fx, Fu = self.step_jac(Zp[:, :nx], Zp[:, nx:], P)
+            Fz = np.concatenate([Fx, Fu], axis=2)  # (n, nx, s)
+            H[:, :, j] = np.einsum("kis,ki->ks", Fz, W).imag / eps
+        return 0.5 * (H + np.swapaxes(H, 1, 2))
 
     # ---- the five CasADi NLP functions ------------------------------------------------
     def nlp_g(self, V, p):
@@ -219,7 +235,7 @@ class Problem:
         lam = np.asarray(lam_g, float).reshape(N, nx)
         W = 2.0 * lam_f * P["Q"] * e + lam
         H = np.zeros((self.NV, self.NV))
-        Hc = self.step_hess(X[:-1], U, P, W) if self.integrator == "euler" else np.zeros((N, s, s))
+        Hc = self.step_hess(X[:-1], U, P, W)
         Fz = np.concatenate([Fx, Fu], axis=2)  # (N,nx,s)
         for k in range(N):
             c0 = k * s

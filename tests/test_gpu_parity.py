@@ -1,6 +1,8 @@
 """Parity tests proper: the CUDA path, called through the C ABI, against the oracle and the golden
 fixtures.  Tolerances are north_star's: 1e-12 relative for rollout/Jacobian/Hessian evaluations,
 1e-6 on controls and 1e-8 relative on the objective for converged solves."""
+import os
+
 import numpy as np
 import pytest
 
@@ -487,8 +489,34 @@ def test_rk4_rollout_and_jacobian_vs_oracle(api, substeps):
     F, Fxo, Fuo = P.step_jac(x, u, {})
     assert H is None
     assert rel(g.T, F - xn) < EVAL_RTOL and rel(Fx.T.reshape(n, 4, 4), Fxo) < EVAL_RTOL and rel(Fu.T.reshape(n, 4, 2), Fuo) < EVAL_RTOL
-    with pytest.raises(api.MmpcError):  # no second derivatives through the integrator
-        m.eval_nodes(x.T.copy(), u.T.copy(), xn.T.copy(), np.ones((4, n)), opts=o)
+    # exact second derivatives through the integrator (forward-over-adjoint on the GPU, complex step in the oracle)
+    w = np.random.default_rng(3).uniform(-1, 1, (n, 4))
+    g2, Fx2, Fu2, H = m.eval_nodes(x.T.copy(), u.T.copy(), xn.T.copy(), w.T.copy(), opts=o)
+    Ho = P.step_hess(x, u, {}, w)
+    iu = np.triu_indices(6)
+    assert np.array_equal(g2, g) or rel(g2, g) < 1e-14
+    assert (np.abs(H.T - Ho[:, iu[0], iu[1]]).max(axis=1) <= 1e-11 * np.abs(Ho).max(axis=(1, 2))).all()
+    with pytest.raises(api.MmpcError):  # more sub-steps than the stage store holds
+        m.eval_nodes(x.T.copy(), u.T.copy(), xn.T.copy(), w.T.copy(), opts=api.default_options(integrator=api.RK4, substeps=5))
+
+
+def test_rk4_hessian_vs_mpmath_golden(api):
+    """F, dF/dz and sum_i w_i d2F_i/dz2 of the RK4 x M interval map against 60-digit mpmath values
+    (tests/golden/rk4_hessian.json, tests/golden/make_rk4_hessian.py; integrator of workingMPC_8_30_21.m:46-59)."""
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "rk4_hessian.json")) as fh:
+        cases = json.load(fh)["cases"]
+    iu = np.triu_indices(6)
+    for c in cases:
+        m = api.Model("double_pendulum", N=4, step_size_us=int(round(c["h"] * 1e6)))
+        o = api.default_options(integrator=api.RK4, substeps=c["substeps"])
+        x = np.array([c["x"]]).T.copy(); u = np.array([c["u"]]).T.copy(); w = np.array([c["w"]]).T.copy()
+        g, Fx, Fu, H = m.eval_nodes(x, u, np.zeros((4, 1)), w, opts=o)
+        Fz = np.concatenate([Fx[:, 0].reshape(4, 4), Fu[:, 0].reshape(4, 2)], axis=1)
+        Hg = np.array(c["H"])
+        assert np.abs(g[:, 0] - c["F"]).max() < 1e-14
+        assert np.abs(Fz - np.array(c["Fz"])).max() <= 1e-13 * np.abs(c["Fz"]).max()
+        assert np.abs(H[:, 0] - Hg[iu]).max() <= 1e-12 * np.abs(Hg).max()
 
 
 def test_rk4_nlp_and_solve_vs_oracle(api):
@@ -507,16 +535,35 @@ def test_rk4_nlp_and_solve_vs_oracle(api):
         assert abs(out["f"][b] - f) <= EVAL_RTOL * abs(f) and rel(out["g"][b], g) < EVAL_RTOL and rel(out["grad_f"][b], gf) < EVAL_RTOL
         for k in range(N):
             assert rel(out["Fx"][b, k], J[k * 4:(k + 1) * 4, k * 6:k * 6 + 4]) < EVAL_RTOL
+    # exact Lagrangian Hessian through the integrator (nlp_hess_l of the prototypes' NLP)
+    lam_g = rng.uniform(-1, 1, (B, P.M))
+    outh = m.nlp_eval(V, p, lam_g, opts=api.default_options(integrator=api.RK4, substeps=2), want=("Hzz",))
+    for b in range(B):
+        Hd = P.nlp_hess_l(V[b], p[b], 1.0, lam_g[b])
+        for k in range(N):  # diagonal node blocks, as test_nlp_eval_vs_oracle maps them for Euler
+            blk = Hd[k * 6:(k + 1) * 6, k * 6:(k + 1) * 6]
+            assert np.abs(outh["Hzz"][b, k] - blk).max() <= 1e-10 * max(1.0, np.abs(blk).max()), (b, k)
     ref = [nlp.solve(P, x0[b], p[b], tol=1e-10, max_iter=400) for b in range(B)]
     assert all(r.status == 0 for r in ref)
-    # default (T3, thread-block tiles), T1 (thread per instance) and T3's 32-instance tile configuration
-    for variant in (0, 1, 3 + 256 * 2):
+    # default (T4), T1 (thread per instance), T3 / T4 with 32-instance tiles; exact Newton: the oracle's iteration counts
+    for variant in (0, 1, 3 + 256 * 2, 4 + 256 * 3):
         s = api.Solver(m, B, tol=1e-9, integrator=api.RK4, substeps=2, kernel_variant=variant)
         s.set_weights(Q, R, Rm)
         Vs, lam, st = s.solve(x0, up, traj)
         assert (st["status"] == 0).all(), (variant, st)
         for b, r in enumerate(ref):
             assert np.abs(Vs[b] - r.V).max() < U_ATOL and abs(st["objective"][b] - r.f) <= OBJ_RTOL * abs(r.f), variant
+            assert abs(int(st["iterations"][b]) - r.iters) <= 1, (variant, st["iterations"], [q.iters for q in ref])
+    # Gauss-Newton on request: the same KKT point, more iterations
+    s = api.Solver(m, B, tol=1e-9, integrator=api.RK4, substeps=2, hessian=api.HESSIAN_GAUSS_NEWTON)
+    s.set_weights(Q, R, Rm)
+    Vg, _, stg = s.solve(x0, up, traj)
+    assert (stg["status"] == 0).all() and stg["iterations"].mean() > st["iterations"].mean()
+    for b, r in enumerate(ref):
+        assert np.abs(Vg[b] - r.V).max() < U_ATOL
+    with pytest.raises(api.MmpcError):
+        api.Solver(m, B, integrator=api.RK4, substeps=8)  # exact Hessian: up to 4 sub-steps
+    api.Solver(m, B, integrator=api.RK4, substeps=8, hessian=api.HESSIAN_GAUSS_NEWTON).close()
 
 
 @pytest.mark.parametrize("plant", ["rk4", "euler"])

@@ -161,3 +161,25 @@ def test_synthetic_batch_is_shardable():
     for x, y in zip(a, b):
         assert np.array_equal(x[32:48], y)
     assert np.abs(a[0][:, :2]).max() <= 0.5 and np.abs(a[0][:, 2:]).max() <= 1.0
+
+
+def test_rk4_hessian_oracle_vs_mpmath_golden():
+    """The oracle's RK4 x M interval map (oracle/nlp.py: step_jac, complex-step step_hess) against 60-digit mpmath values
+    (tests/golden/rk4_hessian.json; integrator of workingMPC_8_30_21.m:46-59): pins the oracle for SURVEY 8 f-4."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "rk4_hessian.json")) as fh:
+        cases = json.load(fh)["cases"]
+    assert len(cases) >= 9
+    for c in cases:
+        P = nlp.Problem(N=2, h=c["h"], integrator="rk4", substeps=c["substeps"])
+        x, u, w = np.array([c["x"]]), np.array([c["u"]]), np.array([c["w"]])
+        F, Fx, Fu = P.step_jac(x, u, {})
+        H = P.step_hess(x, u, {}, w)[0]
+        Fz = np.concatenate([Fx, Fu], axis=2)[0]
+        assert np.abs(F[0] - c["F"]).max() < 1e-14
+        assert np.abs(Fz - np.array(c["Fz"])).max() <= 1e-13 * np.abs(c["Fz"]).max()
+        assert np.abs(H - np.array(c["H"])).max() <= 1e-13 * np.abs(c["H"]).max()
+        # Gauss-Newton option: no integrator second derivatives
+        Pg = nlp.Problem(N=2, h=c["h"], integrator="rk4", substeps=c["substeps"], hessian="gauss_newton")
+        assert not Pg.step_hess(x, u, {}, w).any()
