@@ -42,6 +42,23 @@ WORKLOAD = "BASELINE configs[1]: double pendulum (ex_model_generate), N=50, batc
 print_json = lambda obj: print(json.dumps(obj))
 
 
+def config_of(n_gpus):
+    """The workload description: IDENTICAL in both arms (the driver compares the two dicts)."""
+    return {"workload": WORKLOAD, "model": "double_pendulum", "N": N_NODES, "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus,
+            "start": "cold (zeros, x0 pinned)", "tol": 1e-5, "max_iter": 200}
+
+
+def solve_flops(ops, nx, nu, N, iters_mean):
+    """Algorithmic fp64 flops of one solve: per Newton iteration and node one evaluation of f, A, B and
+    the Hessian contraction (backward sweep), one Riccati stage on the augmented state (x_k, u_{k-1}) and the linear roll-out
+    (forward sweep), one model evaluation for the merit / Armijo test; plus the final convergence sweep."""
+    fl_eval = sum(ops["fABH"]) + sum(ops["fAB"]) + sum(ops["f"])
+    nxa = nx + nu
+    fl_ric = 7 * nxa ** 3 / 3 + 4 * nxa ** 2 * nu + 2 * nxa * nu ** 2 + nu ** 3 / 3
+    fl_fwd = 2 * (nu * (nx + nu) + nx * (nx + nu) + nx * (nx + nu))
+    return iters_mean * N * (fl_eval + fl_ric + fl_fwd) + N * sum(ops["fABH"])
+
+
 def workload(batch, offset=0):
     from mahi_mpc_b200 import workload as w  # synthetic-input generator (SURVEY 8d); identical to the oracle's copy
     x0, up, traj = w.synthetic_batch(NX, NU, N_NODES, H_STEP, batch, offset=offset)
@@ -116,18 +133,22 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU legs (the only places allowed to execute oracle/)
 # ------------------------------------------------------------------------------------------------
-def cpu_solve_rate(sample, opt="O3", threads=0, repeats=1):
-    """solves/s of the CPU restatement on `sample` instances of the bench workload with all host threads."""
+def cpu_solve_rate(sample, opt="O3", threads=0, repeats=1, model="double_pendulum", N=N_NODES, traj_scale=1.0):
+    """solves/s of the CPU restatement on `sample` instances of a bench workload with all host threads (threads = 1: one core)."""
+    from mahi_mpc_b200 import workload as w
     from oracle import coracle, nlp
     co = coracle.COracle(opt)
-    x0, up, traj, (Q, R, Rm) = workload(sample)
-    P = nlp.Problem(N=N_NODES)
+    nx, nu = (8, 4) if model == "arm4" else (NX, NU)
+    x0, up, traj = w.synthetic_batch(nx, nu, N, H_STEP, sample)
+    traj = traj * traj_scale
+    Q, R, Rm = w.default_weights(nx, nu)
+    P = nlp.Problem(model=model, N=N)
     p = np.stack([P.pack_p(traj[b], Q, R, Rm, up[b]) for b in range(sample)])
     nthr = threads or (os.cpu_count() or 1)
     best, conv = None, 0
     for _ in range(repeats):
         t0 = time.perf_counter()
-        _, _, st, bad = co.solve_batch("double_pendulum", N_NODES, H_STEP, False, x0, p, tol=1e-5, max_iter=200, nthreads=nthr)
+        _, _, st, bad = co.solve_batch(model, N, H_STEP, False, x0, p, tol=1e-5, max_iter=200, nthreads=nthr)
         dt = time.perf_counter() - t0
         conv = int((st["status"] == 0).sum())
         best = dt if best is None else min(best, dt)
@@ -152,7 +173,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "model": "double_pendulum", "N": N_NODES, "batch": BATCH, "sample_per_step": sample},
+        "config": config_of(args.gpus), "run": {"sample_per_step": sample, "threads": nthr},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthr, "kind": "port",
                          "sample": f"{sample} of the {BATCH} instances per step, oracle/mpc_oracle.c compiled gcc -O3 "
                                    f"(the reference builds its callbacks -O1, ModelGenerator.cpp:256; -O3 is the faster, conservative baseline), OpenMP over instances; CasADi/IPOPT/MUMPS not installable here"},
@@ -277,21 +298,20 @@ def run_gpu(args):
         # algorithmic bytes per solve: inputs (nx + nu + N nx) + outputs (NV + 5 stats words)
         bytes_per_solve = 8 * (NX + NU + N * NX) + 8 * (model.NV + 5)
         ops = model.op_counts()
-        fl_eval = sum(ops["fABH"]) + sum(ops["fAB"]) + sum(ops["f"])       # backward, forward and merit evaluations of one node
-        nxa = NX + NU
-        fl_ric = 7 * nxa ** 3 / 3 + 4 * nxa ** 2 * NU + 2 * nxa * NU ** 2 + NU ** 3 / 3  # SURVEY 8d flops_riccati
-        fl_fwd = 2 * (NU * (NX + NU) + NX * (NX + NU) + NX * (NX + NU))
-        flops_per_solve = iters_mean * N * (fl_eval + fl_ric + fl_fwd) + N * sum(ops["fABH"])  # + the final convergence sweep
         fp64_peak = api.measure_fp64_peak(local)
-        roofline = {"bound": "hbm", "achieved": B * bytes_per_solve / kern_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": B * bytes_per_solve / kern_s / 1e9 / hbm_peak, "traffic": ncu_traffic("solve_kernel_t3"), "peak_source": peak_src,
-                    "kernel": "solve_kernel", "note": "the solve is FP64-pipe/latency bound, not HBM bound (SURVEY 8d): see fp64_roofline"}
-        fp64 = {"bound": "fp64-dfma", "achieved": B * flops_per_solve / kern_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": B * flops_per_solve / kern_s / 1e12 / fp64_peak if fp64_peak else None,
-                "peak_source": "measured in this run (mmpc_measure_fp64_peak: independent DFMA chains)",
-                "algorithmic_flops_per_solve": flops_per_solve}
+        flops_per_solve = solve_flops(ops, NX, NU, N, iters_mean)
+        hbm = {"bound": "hbm", "achieved": B * bytes_per_solve / kern_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+               "frac": B * bytes_per_solve / kern_s / 1e9 / hbm_peak, "peak_source": peak_src, "algorithmic_bytes_per_solve": bytes_per_solve}
+        # the solve is bound by the fp64 pipe / its dependent chains, not by HBM: THE roofline of this kernel is fp64
+        roofline = {"bound": "fp64", "achieved": B * flops_per_solve / kern_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": B * flops_per_solve / kern_s / 1e12 / fp64_peak if fp64_peak else None,
+                    "traffic": ncu_traffic("solve_kernel_t4"), "kernel": "solve_kernel_t4<double_pendulum, 32, 7, 5>",
+                    "peak_source": "measured in this run (mmpc_measure_fp64_peak: independent DFMA chains on every SM)",
+                    "algorithmic_flops_per_solve": flops_per_solve, "hbm": hbm}
+        fp64 = dict(roofline)  # round-1 key, kept for continuity
         extras = node_eval_bench(api, model, dev, hbm_peak) if world == 1 else None
-        lat = latency_bench(api, dev) if world == 1 else None
+        lat = latency_bench(api, dev, with_cpu=not args.no_cpu) if world == 1 else None
+        others = other_configs(api, dev, fp64_peak, with_cpu=not args.no_cpu) if world == 1 and not args.headline_only else None
         cpu = None
         if world == 1 and not args.no_cpu:
             r0, nthr, _, _ = cpu_solve_rate(128, "O3")
@@ -304,15 +324,14 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "model": "double_pendulum", "N": N, "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": f"instances sharded over {world} GPU(s), no collective on the solve path",
-                       "l2": "flushed between timed steps (256 MB write outside the event pair)",
-                       "kernel_variant": args.variant, "tol": 1e-5, "max_iter": 200},
+            "config": config_of(world),
+            "run": {"parallelism": f"instances sharded over {world} GPU(s), no collective on the solve path",
+                    "l2": "flushed between timed steps (256 MB write outside the event pair)", "kernel_variant": args.variant},
             "converged_fraction": conv_frac, "iterations_mean": iters_mean,
             "node_evals_per_s": value * N * (2 * iters_mean + 1),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "fp64_roofline": fp64,
-            "cpu_baseline": cpu, "node_eval": extras, "latency": lat, "gather_ms": gather_ms,
+            "cpu_baseline": cpu, "node_eval": extras, "latency": lat, "gather_ms": gather_ms, "other_configs": others,
         }
         print_json(line)
     if world > 1:
@@ -345,8 +364,10 @@ def node_eval_bench(api, model, dev, hbm_peak):
                          "frac": n * bytes_per_node / t / 1e9 / hbm_peak, "traffic": ncu_traffic("eval_nodes_kernel"), "bytes_per_node": bytes_per_node}}
 
 
-def latency_bench(api, dev):
-    """p50 single-solve latency, B = 1, N = 25 closed-loop setting of config 1 (host pointers, cold start)."""
+def latency_bench(api, dev, with_cpu=True):
+    """p50 single-solve latency, B = 1, N = 25 closed-loop setting of config 1 (host pointers, cold start), next to the CPU
+    restatement's single-thread latency on this box (the reference's budget is a 1 kHz loop,
+    thread_model_control_example.cpp:70-71)."""
     N = 25
     from mahi_mpc_b200 import workload as w
     x0, up, traj = w.synthetic_batch(NX, NU, N, H_STEP, 1)
@@ -355,13 +376,75 @@ def latency_bench(api, dev):
     s = api.Solver(m, 1, device=dev.index or 0, warm_start=0)
     s.set_weights(Q, R, Rm)
     ts = []
-    for i in range(60):
+    for i in range(110):
         t0 = time.perf_counter()
         s.solve(x0, up, traj, want_lam=False)
         ts.append(time.perf_counter() - t0)
     ts = sorted(ts[10:])
-    return {"workload": "B=1, N=25, cold start, host pointers (one ModelControl::calc_u)", "p50_us": 1e6 * ts[len(ts) // 2],
-            "p99_us": 1e6 * ts[-1]}
+    out = {"workload": "B=1, N=25, cold start, host pointers (one ModelControl::calc_u)", "p50_us": 1e6 * ts[len(ts) // 2],
+           "p99_us": 1e6 * ts[-1], "kernel_us": 1e3 * s.last_timing()["kernel_ms"]}
+    if with_cpu:
+        from oracle import coracle, nlp
+        co = coracle.COracle("O3")
+        P = nlp.Problem(N=N)
+        p = np.stack([P.pack_p(traj[0], Q, R, Rm, up[0])])
+        tc = []
+        for i in range(110):
+            t0 = time.perf_counter()
+            co.solve_batch("double_pendulum", N, H_STEP, False, x0, p, tol=1e-5, max_iter=200, nthreads=1)
+            tc.append(time.perf_counter() - t0)
+        tc = sorted(tc[10:])
+        out["cpu_port_p50_us"] = 1e6 * tc[len(tc) // 2]
+        out["cpu_port_p99_us"] = 1e6 * tc[-1]
+        out["faster_for_one_solve"] = "cpu port (one core)" if out["cpu_port_p50_us"] < out["p50_us"] else "gpu"
+    return out
+
+
+def other_configs(api, dev, fp64_peak, with_cpu=True):
+    """BASELINE configs[2] (4-DOF arm, N = 50, batch 16384: here on ONE GPU, the multi-GPU runs are tools/config3_multi.py) and
+    configs[3] (horizon sweep N = 10/50/100/200 at batch 4096), each with its fp64 roofline fraction; bounded to a few seconds."""
+    import torch
+    from mahi_mpc_b200 import workload as w
+
+    def timed(model_name, nx, nu, N, B, reps, traj_scale=1.0):
+        x0, up, traj = w.synthetic_batch(nx, nu, N, H_STEP, B)
+        traj = traj * traj_scale
+        Q, R, Rm = w.default_weights(nx, nu)
+        m = api.Model(model_name, N=N)
+        s = api.Solver(m, B, device=dev.index or 0, warm_start=0)
+        s.set_weights(Q, R, Rm)
+        d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (x0, up, traj)]
+        V = torch.empty(B, m.NV, dtype=torch.float64, device=dev)
+        st = torch.empty(B, 5, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            s.solve(*d, V_out=V, stats_out=st, want_lam=False)
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); s.solve(*d, V_out=V, stats_out=st, want_lam=False); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        stats = api.stats_from_tensor(st)
+        ms = statistics.median(ts)
+        conv = float((stats["status"] == 0).sum())
+        it = float(stats["iterations"].mean())
+        fl = solve_flops(m.op_counts(), nx, nu, N, it)
+        ach = B * fl / (ms * 1e-3) / 1e12
+        out = {"model": model_name, "N": N, "batch": B, "ms": ms, "solves_per_s": conv / ms * 1e3, "converged_fraction": conv / B,
+               "iterations_mean": it, "node_evals_per_s": conv / ms * 1e3 * N * (2 * it + 1),
+               "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None,
+                            "algorithmic_flops_per_solve": fl}}
+        s.close()
+        return out
+
+    res = {"horizon_sweep": [timed("double_pendulum", NX, NU, N, BATCH, 5) for N in (10, 50, 100, 200)]}
+    c3 = timed("arm4", 8, 4, 50, 16384, 3, traj_scale=0.5)
+    c3["workload"] = "BASELINE configs[2]: 4-DOF arm with torque cost, N=50, batch 16384 on ONE GPU (2/4/8 GPUs: tools/config3_multi.py, profiles/)"
+    if with_cpu:
+        rate, nthr, dt, conv = cpu_solve_rate(256, "O3", model="arm4", N=50, traj_scale=0.5)
+        c3["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": nthr, "kind": "port",
+                              "sample": f"256 of the 16384 instances, oracle/mpc_oracle.c + oracle/arm4_jets.c gcc -O3, {dt:.1f} s"}
+    res["config3_arm4"] = c3
+    return res
 
 
 def main():
@@ -372,6 +455,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="solve kernel variant (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--headline-only", action="store_true", help="skip the other BASELINE configs (horizon sweep, 4-DOF arm)")
     args = ap.parse_args()
     # Libraries (NCCL prints its version banner) write to fd 1; the contract wants exactly ONE JSON line on stdout.
     # Route fd 1 to stderr for the duration of the run and emit the JSON line on the real stdout.
