@@ -15,6 +15,7 @@
 
 struct mmpc_model;
 struct mmpc_solver;
+struct mmpc_group;
 
 namespace mahi {
 namespace mpc {
@@ -84,6 +85,10 @@ class BatchModelControl {
 public:
     BatchModelControl(std::string model_name, int batch, std::vector<double> Q = {}, std::vector<double> R = {},
                       std::vector<double> Rm = {}, casadi::Dict solver_opts = casadi::Dict(), int device = 0);
+    /// The batch sharded over several GPUs of one box (contiguous shards, one solver handle per device, no collective on
+    /// the solve path; calc_u gathers every shard's plans into the same flat vector).
+    BatchModelControl(std::string model_name, int batch, std::vector<int> devices, std::vector<double> Q = {}, std::vector<double> R = {},
+                      std::vector<double> Rm = {}, casadi::Dict solver_opts = casadi::Dict());
     ~BatchModelControl();
     BatchModelControl(const BatchModelControl&) = delete;
     BatchModelControl& operator=(const BatchModelControl&) = delete;
@@ -103,6 +108,7 @@ public:
 private:
     mmpc_model* m_model = nullptr;
     mmpc_solver* m_solver = nullptr;
+    mmpc_group* m_group = nullptr;  // several devices: shards behind one group handle
     int m_batch, m_nv = 0;
     std::vector<double> m_V;
     std::vector<int> m_iters, m_status;

@@ -196,10 +196,38 @@ int mmpc_closed_loop(mmpc_solver_t solver, int cycles, int plant_integrator, dou
                      double* X_log, double* U_log, int* iters_log, mmpc_mem mem, void* stream);
 
 /* Time of the device work of the last mmpc_solve on this handle in milliseconds (CUDA events on the
- * launching stream): [0] H2D staging, [1] kernels, [2] D2H staging. */
+ * launching stream): [0] H2D staging, [1] kernels, [2] D2H staging.  Host-buffer calls that are pipelined over sub-batches
+ * (batches >= 4096) report the whole H2D + solve + D2H span in [1] and zeros in [0], [2].
+ * Tracing: every entry point opens an NVTX range ("mmpc_solve", ...); with MMPC_STATS_JSONL=<path> in the environment every
+ * host-buffer mmpc_solve that returns statistics appends one JSON line (batch, N, kernel variant, times, iteration and
+ * status counts) to <path>. */
 int mmpc_last_timing(mmpc_solver_t solver, double ms[3]);
 /* number of kernels the last mmpc_solve launched */
 int mmpc_last_launch_count(mmpc_solver_t solver, int* launches);
+
+/* ---- several GPUs in one process -------------------------------------------------------------
+ * Independent MPC instances shard trivially (BASELINE north_star): a group owns one solver handle per
+ * device, each holding a contiguous shard of `batch_total` instances (the first batch_total % n shards are one longer).
+ * There is no collective on the solve path; the only cross-device traffic is the gather of plans and statistics.
+ * `devices` may name a device more than once (several shards on one GPU).  The reference has no counterpart: its
+ * ModelControl solves one instance on one CPU thread (ModelControl.cpp:116-172). */
+typedef struct mmpc_group* mmpc_group_t;
+int mmpc_group_create(mmpc_model_t model, const int* devices, int n_devices, int batch_total, const mmpc_options* opts, mmpc_group_t* out);
+int mmpc_group_free(mmpc_group_t group);
+/* shard i: its device, first instance and instance count; its handle (for per-shard calls such as mmpc_set_bounds) */
+int mmpc_group_shard(mmpc_group_t group, int i, int* device, int* offset, int* count, mmpc_solver_t* solver);
+int mmpc_group_size(mmpc_group_t group, int* n_shards, int* batch_total);
+/* weights shared by all instances (as mmpc_set_weights with per_instance = 0) / control and state limits, on every shard */
+int mmpc_group_set_weights(mmpc_group_t group, const double* Q, const double* R, const double* Rm);
+int mmpc_group_set_bounds(mmpc_group_t group, const double* x_min, const double* x_max, const double* u_min, const double* u_max);
+/* mmpc_solve over all shards concurrently, HOST buffers of the whole batch (layouts of mmpc_solve): every device copies its
+ * shard in, solves, and copies its plans / multipliers / statistics straight into the caller's arrays -- the gather to the host. */
+int mmpc_group_solve(mmpc_group_t group, const double* state, const double* control, const double* traj, double* V_out,
+                     double* lam_out, mmpc_stats* stats);
+/* Gather of the last mmpc_group_solve's plans and statistics to ONE device (peer-to-peer copies over NVLink where the
+ * devices allow it): V_root[batch_total*NV] and stats_root[batch_total] (may be NULL) are DEVICE pointers on `root_device`.
+ * ms_out (may be NULL): duration of the copies on the root device, CUDA events. */
+int mmpc_group_gather(mmpc_group_t group, int root_device, double* V_root, mmpc_stats* stats_root, double* ms_out);
 
 /* ---- measurement utility ----------------------------------------------------------------------
  * Measured fp64 FMA throughput of `device` in TFLOP/s (independent DFMA chains, every SM busy,

@@ -57,7 +57,8 @@ ABI_SYMBOLS = [
     "mmpc_model_op_counts", "mmpc_linearise", "mmpc_eval_nodes", "mmpc_nlp_eval", "mmpc_solver_create",
     "mmpc_solver_free", "mmpc_solver_batch", "mmpc_set_options", "mmpc_set_weights", "mmpc_set_bounds",
     "mmpc_reset_warm_start", "mmpc_solve", "mmpc_last_timing", "mmpc_last_launch_count", "mmpc_measure_fp64_peak",
-    "mmpc_closed_loop",
+    "mmpc_closed_loop", "mmpc_group_create", "mmpc_group_free", "mmpc_group_shard", "mmpc_group_size", "mmpc_group_set_weights",
+    "mmpc_group_set_bounds", "mmpc_group_solve", "mmpc_group_gather",
 ]
 
 _lib = None
@@ -73,6 +74,14 @@ def lib():
         L.mmpc_last_error.restype = C.c_char_p
         vp = C.c_void_p
         L.mmpc_model_create.argtypes = [C.POINTER(ModelParams), C.POINTER(vp)]
+        L.mmpc_group_create.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(Options), C.POINTER(vp)]
+        L.mmpc_group_free.argtypes = [vp]
+        L.mmpc_group_size.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.mmpc_group_shard.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(vp)]
+        L.mmpc_group_set_weights.argtypes = [vp, _dp, _dp, _dp]
+        L.mmpc_group_set_bounds.argtypes = [vp, _dp, _dp, _dp, _dp]
+        L.mmpc_group_solve.argtypes = [vp, _dp, _dp, _dp, _dp, _dp, C.POINTER(Stats)]
+        L.mmpc_group_gather.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_double)]
         L.mmpc_model_load.argtypes = [C.c_char_p, C.POINTER(vp)]
         L.mmpc_model_free.argtypes = [vp]
         L.mmpc_model_dims.argtypes = [vp] + [C.POINTER(C.c_int)] * 6
@@ -348,6 +357,56 @@ class Solver:
         n = C.c_int()
         _ck(lib().mmpc_last_launch_count(self._h, C.byref(n)))
         return n.value
+
+
+class Group:
+    """mmpc_group_*: one batch sharded over several devices of one process (contiguous shards, no collective on the solve path)."""
+
+    def __init__(self, model: Model, batch_total: int, devices, **opts):
+        self.model, self.batch = model, int(batch_total)
+        self.opts = default_options(**opts)
+        self._h = C.c_void_p()
+        dv = (C.c_int * len(devices))(*devices)
+        _ck(lib().mmpc_group_create(model._h, dv, len(devices), self.batch, C.byref(self.opts), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().mmpc_group_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shards(self):
+        n, tot = C.c_int(), C.c_int()
+        _ck(lib().mmpc_group_size(self._h, C.byref(n), C.byref(tot)))
+        out = []
+        for i in range(n.value):
+            d, o, c = C.c_int(), C.c_int(), C.c_int()
+            _ck(lib().mmpc_group_shard(self._h, i, C.byref(d), C.byref(o), C.byref(c), None))
+            out.append((d.value, o.value, c.value))
+        return out
+
+    def set_weights(self, Q, R, Rm):
+        q, r, rm = (np.ascontiguousarray(a, np.float64) for a in (Q, R, Rm))
+        _ck(lib().mmpc_group_set_weights(self._h, q.ctypes.data_as(_dp), r.ctypes.data_as(_dp), rm.ctypes.data_as(_dp)))
+
+    def solve(self, state, control, traj, want_lam=True):
+        m, B = self.model, self.batch
+        state, control, traj = (np.ascontiguousarray(a, np.float64) for a in (state, control, traj))
+        V = np.empty((B, m.NV)); lam = np.empty((B, m.M)) if want_lam else None
+        st = np.empty(B, STATS_DTYPE)
+        _ck(lib().mmpc_group_solve(self._h, state.ctypes.data_as(_dp), control.ctypes.data_as(_dp), traj.ctypes.data_as(_dp), V.ctypes.data_as(_dp),
+                                   lam.ctypes.data_as(_dp) if want_lam else None, st.ctypes.data_as(C.POINTER(Stats))))
+        return V, lam, st
+
+    def gather(self, root_device, V_root_ptr, stats_root_ptr=None):
+        ms = C.c_double()
+        _ck(lib().mmpc_group_gather(self._h, int(root_device), C.c_void_p(V_root_ptr), C.c_void_p(stats_root_ptr) if stats_root_ptr else None, C.byref(ms)))
+        return ms.value
 
 
 def stats_from_tensor(t):

@@ -226,7 +226,27 @@ BatchModelControl::BatchModelControl(std::string model_name, int batch, std::vec
     m_status.assign(batch, 0);
 }
 
+BatchModelControl::BatchModelControl(std::string model_name, int batch, std::vector<int> devices, std::vector<double> Q, std::vector<double> R,
+                                     std::vector<double> Rm, casadi::Dict solver_opts)
+    : m_batch(batch) {
+    model_parameters = read_parameters(model_name);
+    check(mmpc_model_load(model_name.c_str(), &m_model), "mmpc_model_load");
+    const mmpc_options o = options_from(solver_opts);
+    const int rc = mmpc_group_create(m_model, devices.data(), static_cast<int>(devices.size()), batch, &o, &m_group);
+    if (rc != MMPC_OK) {
+        mmpc_model_free(m_model);
+        check(rc, "mmpc_group_create");
+    }
+    default_weights(model_parameters, Q, R, Rm);
+    check(mmpc_group_set_weights(m_group, Q.data(), R.data(), Rm.data()), "mmpc_group_set_weights");
+    check(mmpc_model_dims(m_model, nullptr, nullptr, nullptr, &m_nv, nullptr, nullptr), "mmpc_model_dims");
+    m_V.assign(static_cast<size_t>(batch) * m_nv, 0.0);
+    m_iters.assign(batch, 0);
+    m_status.assign(batch, 0);
+}
+
 BatchModelControl::~BatchModelControl() {
+    if (m_group) mmpc_group_free(m_group);
     if (m_solver) mmpc_solver_free(m_solver);
     if (m_model) mmpc_model_free(m_model);
 }
@@ -237,7 +257,8 @@ const std::vector<double>& BatchModelControl::calc_u(const std::vector<double>& 
     if (states.size() != B * nx || controls.size() != B * nu || trajs.size() != B * N * nx)
         throw std::invalid_argument("BatchModelControl::calc_u: need batch*num_x, batch*num_u, batch*num_shooting_nodes*num_x entries");
     std::vector<mmpc_stats> st(B);
-    check(mmpc_solve(m_solver, states.data(), controls.data(), trajs.data(), m_V.data(), nullptr, st.data(), MMPC_MEM_HOST, nullptr), "mmpc_solve");
+    if (m_group) check(mmpc_group_solve(m_group, states.data(), controls.data(), trajs.data(), m_V.data(), nullptr, st.data()), "mmpc_group_solve");
+    else check(mmpc_solve(m_solver, states.data(), controls.data(), trajs.data(), m_V.data(), nullptr, st.data(), MMPC_MEM_HOST, nullptr), "mmpc_solve");
     for (size_t b = 0; b < B; ++b) {
         m_iters[b] = st[b].iterations;
         m_status[b] = st[b].status;
@@ -252,19 +273,30 @@ std::vector<double> BatchModelControl::first_control(int b) const {
 }
 
 void BatchModelControl::update_weights(std::vector<double> Q, std::vector<double> R, std::vector<double> Rm) {
-    check(mmpc_set_weights(m_solver, Q.empty() ? nullptr : Q.data(), R.empty() ? nullptr : R.data(), Rm.empty() ? nullptr : Rm.data(), 0),
-          "mmpc_set_weights");
+    const double *q = Q.empty() ? nullptr : Q.data(), *r = R.empty() ? nullptr : R.data(), *rm = Rm.empty() ? nullptr : Rm.data();
+    if (m_group) check(mmpc_group_set_weights(m_group, q, r, rm), "mmpc_group_set_weights");
+    else check(mmpc_set_weights(m_solver, q, r, rm, 0), "mmpc_set_weights");
 }
 
 void BatchModelControl::update_control_limits(std::vector<double> u_min, std::vector<double> u_max) {
     if (static_cast<int>(u_min.size()) != model_parameters.num_u || static_cast<int>(u_max.size()) != model_parameters.num_u)
         throw std::invalid_argument("update_control_limits: need num_u entries");
-    check(mmpc_set_bounds(m_solver, nullptr, nullptr, u_min.data(), u_max.data()), "mmpc_set_bounds");
+    if (m_group) check(mmpc_group_set_bounds(m_group, nullptr, nullptr, u_min.data(), u_max.data()), "mmpc_group_set_bounds");
+    else check(mmpc_set_bounds(m_solver, nullptr, nullptr, u_min.data(), u_max.data()), "mmpc_set_bounds");
     model_parameters.u_min = std::move(u_min);
     model_parameters.u_max = std::move(u_max);
 }
 
-void BatchModelControl::reset_warm_start() { check(mmpc_reset_warm_start(m_solver), "mmpc_reset_warm_start"); }
+void BatchModelControl::reset_warm_start() {
+    if (!m_group) { check(mmpc_reset_warm_start(m_solver), "mmpc_reset_warm_start"); return; }
+    int n = 0;
+    check(mmpc_group_size(m_group, &n, nullptr), "mmpc_group_size");
+    for (int i = 0; i < n; ++i) {
+        mmpc_solver* s = nullptr;
+        check(mmpc_group_shard(m_group, i, nullptr, nullptr, nullptr, &s), "mmpc_group_shard");
+        check(mmpc_reset_warm_start(s), "mmpc_reset_warm_start");
+    }
+}
 
 }  // namespace mpc
 }  // namespace mahi

@@ -633,3 +633,55 @@ def test_max_iter_is_honoured_and_reported(api):
     s.set_options(max_iter=200, tol=1e-5)
     V, lam, st = s.solve(x0, up, traj)
     assert (st["status"] == 0).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# several devices in one process (mmpc_group_*), the packed small-batch staging path, observability
+# ---------------------------------------------------------------------------------------------------------------
+def test_group_solve_shards_and_gathers(api):
+    """mmpc_group_solve: the batch cut into contiguous shards (here three handles on device 0 -- the driver box of the
+    parity tests has one GPU; tools/config3_multi.py and bench.py --gpus N exercise one process per GPU), every shard's plans
+    land in the caller's arrays, and mmpc_group_gather collects them on one device.  Same results as ONE handle."""
+    import torch
+    N, B = 25, 70
+    P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B)
+    m = api.Model("double_pendulum", N=N)
+    s = api.Solver(m, B, tol=1e-10, warm_start=0); s.set_weights(Q, R, Rm)
+    V1, lam1, st1 = s.solve(x0, up, traj)
+    g = api.Group(m, B, [0, 0, 0], tol=1e-10, warm_start=0); g.set_weights(Q, R, Rm)
+    assert g.shards() == [(0, 0, 24), (0, 24, 23), (0, 47, 23)]  # mahi_mpc_b200/shard.py's partition
+    Vg, lamg, stg = g.solve(x0, up, traj)
+    assert (stg["status"] == 0).all() and np.array_equal(stg["iterations"], st1["iterations"])
+    assert np.abs(Vg - V1).max() < 1e-12 and np.abs(lamg - lam1).max() < 1e-9
+    Vd = torch.zeros(B, m.NV, dtype=torch.float64, device="cuda:0")
+    std = torch.zeros(B, 5, dtype=torch.float64, device="cuda:0")
+    ms = g.gather(0, Vd.data_ptr(), std.data_ptr())
+    assert ms >= 0.0 and np.array_equal(Vd.cpu().numpy(), Vg)
+    assert np.array_equal(api.stats_from_tensor(std)["iterations"], stg["iterations"])
+    with pytest.raises(api.MmpcError):
+        api.Group(m, 2, [0, 0, 0])  # fewer instances than shards
+
+
+def test_small_batch_packed_staging_and_stats_jsonl(api, coracle, tmp_path):
+    """B = 1 (one ModelControl::calc_u): the packed pinned staging path gives the oracle's plan; mmpc_last_timing reports
+    the three phases; MMPC_STATS_JSONL appends one line per solve."""
+    import json, subprocess, sys
+    N = 25
+    P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, 1)
+    Vo, _, sto, bad = coracle.solve_batch("double_pendulum", N, P.h, False, x0, p, tol=1e-10)
+    m = api.Model("double_pendulum", N=N)
+    s = api.Solver(m, 1, tol=1e-10, warm_start=0); s.set_weights(Q, R, Rm)
+    V, lam, st = s.solve(x0, up, traj)
+    assert st["status"][0] == 0 and np.abs(V - Vo).max() < U_ATOL
+    t = s.last_timing()
+    assert t["h2d_ms"] > 0 and t["kernel_ms"] > 0 and t["d2h_ms"] > 0
+    # the environment variable is read once per process: a child process writes the file
+    out = tmp_path / "stats.jsonl"
+    code = ("import numpy as np, mahi_mpc_b200.api as api; from mahi_mpc_b200 import workload as w;"
+            "x0, up, traj = w.synthetic_batch(4, 2, 25, 0.002, 5); Q, R, Rm = w.default_weights(4, 2);"
+            "m = api.Model('double_pendulum', N=25); s = api.Solver(m, 5, warm_start=0); s.set_weights(Q, R, Rm);"
+            "s.solve(x0, up, traj); s.solve(x0, up, traj)")
+    env = dict(os.environ, MMPC_STATS_JSONL=str(out))
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    lines = [json.loads(l) for l in out.read_text().splitlines()]
+    assert len(lines) == 2 and lines[0]["batch"] == 5 and lines[0]["converged"] == 5 and lines[0]["kernel_ms"] > 0 and lines[0]["N"] == 25
