@@ -49,6 +49,12 @@ typedef enum mmpc_integrator { MMPC_EULER = 0, MMPC_RK4 = 1 } mmpc_integrator;
  * IPOPT in the prototypes, workingMPC_8_30_21.m:46-59,109-112; up to 4 sub-steps); GAUSS_NEWTON keeps the objective's
  * first-order part only (same KKT point, linear convergence).  Euler / linearised shooting is always exact. */
 typedef enum mmpc_hessian { MMPC_HESSIAN_EXACT = 0, MMPC_HESSIAN_GAUSS_NEWTON = 1 } mmpc_hessian;
+/* Where the tracking error of the objective sits.  SHOOTING: on the one-step map, e_k = F(x_k,u_k) - r_k -- the library's NLP
+ * (ModelGenerator.cpp:207-214).  NODE: on the decision variable, e_k = x_{k+1} - r_k -- the MATLAB prototypes' NLP
+ * (workingMPC_8_30_21.m:90-106: the error of x(:,k) against the reference at its own time; there Q <- 1000 Q, no du term and
+ * Rm <- R; x_0 is pinned, so its term is a constant and is left out).  Same minimisers on the feasible set, a different
+ * Lagrangian (constant 2Q blocks, no sum 2Q e_i d2F_i term).  NODE runs on T4 / T1. */
+typedef enum mmpc_cost { MMPC_COST_SHOOTING = 0, MMPC_COST_NODE = 1 } mmpc_cost;
 
 /* per-instance solve status (the reference never inspects IPOPT's, ModelControl.cpp:159-160) */
 typedef enum mmpc_solve_status {
@@ -93,7 +99,8 @@ typedef struct mmpc_options {
                               tile configuration (mmpc_solve_t3.cuh, mmpc_solve_t4.cuh) -- experiments and tests only.
                               Changing it forgets the warm start. */
     int hessian;           /* MMPC_HESSIAN_EXACT (default) / MMPC_HESSIAN_GAUSS_NEWTON: RK4 shooting only */
-    int reserved[7];
+    int cost;              /* MMPC_COST_SHOOTING (default, the library's objective) / MMPC_COST_NODE (the prototypes') */
+    int reserved[6];
 } mmpc_options;
 
 /* Per-instance statistics returned by mmpc_solve (40 bytes). */

@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(PKG, "lib", "libmahi_mpc_b200.so")
 MEM_HOST, MEM_DEVICE = 0, 1
 EULER, RK4 = 0, 1
 HESSIAN_EXACT, HESSIAN_GAUSS_NEWTON = 0, 1
+COST_SHOOTING, COST_NODE = 0, 1
 _dp = C.POINTER(C.c_double)
 
 
@@ -38,7 +39,7 @@ class ModelParams(C.Structure):
 class Options(C.Structure):
     _fields_ = [("tol", C.c_double), ("max_iter", C.c_int), ("integrator", C.c_int), ("substeps", C.c_int),
                 ("mu_init", C.c_double), ("warm_start", C.c_int), ("warm_start_duals", C.c_int),
-                ("kernel_variant", C.c_int), ("hessian", C.c_int), ("reserved", C.c_int * 7)]
+                ("kernel_variant", C.c_int), ("hessian", C.c_int), ("cost", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class Stats(C.Structure):

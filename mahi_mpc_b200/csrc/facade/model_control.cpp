@@ -36,6 +36,12 @@ mmpc_options options_from(const casadi::Dict& d) {
         else if (kv.first == "ipopt.mu_init" || kv.first == "mu_init") o.mu_init = kv.second.to_double();
         else if (kv.first == "warm_start_duals") o.warm_start_duals = kv.second.to_int();
         else if (kv.first == "kernel_variant") o.kernel_variant = kv.second.to_int();
+        else if (kv.first == "device") continue;  // read by the constructor
+        // extensions beyond the library's NLP: the MATLAB prototypes' integrator, Hessian and objective (mahi_mpc_b200.h)
+        else if (kv.first == "integrator") o.integrator = kv.second.to_int();      // MMPC_EULER / MMPC_RK4
+        else if (kv.first == "substeps") o.substeps = kv.second.to_int();
+        else if (kv.first == "hessian") o.hessian = kv.second.to_int();            // MMPC_HESSIAN_EXACT / _GAUSS_NEWTON
+        else if (kv.first == "cost") o.cost = kv.second.to_int();                  // MMPC_COST_SHOOTING / _NODE
     }
     return o;
 }
@@ -75,7 +81,9 @@ void ModelControl::load_model(const std::string& model_name) {
     model_parameters = read_parameters(model_name);
     check(mmpc_model_load(model_name.c_str(), &m_model), "mmpc_model_load");
     const mmpc_options o = options_from(m_solver_opts);
-    check(mmpc_solver_create(m_model, 0, 1, &o, &m_solver), "mmpc_solver_create");
+    int device = 0;  // solver_opts["device"]: which GPU this controller solves on (one ModelControl per device is fine)
+    for (const auto& kv : m_solver_opts) if (kv.first == "device") device = kv.second.to_int();
+    check(mmpc_solver_create(m_model, device, 1, &o, &m_solver), "mmpc_solver_create");
     default_weights(model_parameters, m_Q, m_R, m_Rm);
     m_weights_dirty = true;
     int nv = 0;

@@ -360,14 +360,16 @@ __global__ void __launch_bounds__(128) nlp_eval_kernel(mmpc_problem P, int B, co
     const int NV = NX * (N + 1) + NU * N, Mc = N * NX;
     const double* Vb = V + (size_t)b * NV;
     const PView<M> pv(p + (size_t)b * PView<M>::np(N, P.is_linear), N, P.is_linear);
-    double x[NX], u[NU], up[NU], xn[NX], r[NX], lam[NX], wq[NX], F[NX], fx[NX * NX], fu[NX * NU], hs[NH], e[NX];
+    double x[NX], u[NU], up[NU], xn[NX], r[NX], lam[NX], wq[NX], wqh[NX], F[NX], fx[NX * NX], fu[NX * NU], hs[NH], e[NX];
     MMPC_UNROLL for (int i = 0; i < NX; ++i) {
         x[i] = Vb[k * S + i];
         xn[i] = Vb[(k + 1) * S + i];
         r[i] = pv.r[k * NX + i];
         lam[i] = lamg ? lamg[(size_t)b * Mc + k * NX + i] : 0.0;
         wq[i] = 2.0 * lam_f * pv.Q[i];
+        wqh[i] = P.node_cost ? 0.0 : wq[i];  // MMPC_COST_NODE: the tracking term does not see F, the Hessian weights are lam alone
     }
+    const bool node = P.node_cost != 0;
     MMPC_UNROLL for (int j = 0; j < NU; ++j) {
         u[j] = Vb[k * S + NX + j];
         up[j] = k ? Vb[(k - 1) * S + NX + j] : pv.u_init[j];
@@ -381,17 +383,17 @@ __global__ void __launch_bounds__(128) nlp_eval_kernel(mmpc_problem P, int B, co
         step_linear<M, 2>(P.h, x, u, A, Bm, pv.xdot_init, pv.x_init, pv.u_init, F, fx, fu, hs);
     } else if (P.integrator == MMPC_RK4) {
         if (Hzz && !P.gauss_newton) {
-            step_rk4_hess<M>(P.h, P.substeps, x, u, wq, r, lam, F, fx, fu, hs);
+            step_rk4_hess<M>(P.h, P.substeps, x, u, wqh, r, lam, F, fx, fu, hs);
         } else {
             step_rk4<M, 1>(P.h, P.substeps, x, u, F, fx, fu);
             MMPC_UNROLL for (int i = 0; i < NH; ++i) hs[i] = 0.0;  // Gauss-Newton part only
         }
     } else {
-        step_euler<M, 2>(P.h, x, u, wq, r, lam, F, fx, fu, hs);
+        step_euler<M, 2>(P.h, x, u, wqh, r, lam, F, fx, fu, hs);
     }
     double fk = 0.0;
     MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-        e[i] = F[i] - r[i];
+        e[i] = (node ? xn[i] : F[i]) - r[i];
         fk = fma(pv.Q[i] * e[i], e[i], fk);
         if (g) g[(size_t)b * Mc + k * NX + i] = F[i] - xn[i];
     }
@@ -407,17 +409,18 @@ __global__ void __launch_bounds__(128) nlp_eval_kernel(mmpc_problem P, int B, co
         double* gb = grad_f + (size_t)b * NV;
         MMPC_UNROLL for (int j = 0; j < NX; ++j) {
             double a = 0.0;
-            MMPC_UNROLL for (int i = 0; i < NX; ++i) a = fma(fx[i * NX + j], 2.0 * pv.Q[i] * e[i], a);
+            if (node) a = k ? 2.0 * pv.Q[j] * (x[j] - pv.r[(k - 1) * NX + j]) : 0.0;  // d/dx_k of (x_k - r_{k-1})' Q (x_k - r_{k-1})
+            else MMPC_UNROLL for (int i = 0; i < NX; ++i) a = fma(fx[i * NX + j], 2.0 * pv.Q[i] * e[i], a);
             gb[k * S + j] = a;  // x_k gets a contribution from node k only
         }
         MMPC_UNROLL for (int j = 0; j < NU; ++j) {
             double a = 0.0;
-            MMPC_UNROLL for (int i = 0; i < NX; ++i) a = fma(fu[i * NU + j], 2.0 * pv.Q[i] * e[i], a);
+            if (!node) MMPC_UNROLL for (int i = 0; i < NX; ++i) a = fma(fu[i * NU + j], 2.0 * pv.Q[i] * e[i], a);
             const double du = u[j] - up[j];
             atomicAdd(&gb[k * S + NX + j], a + 2.0 * pv.R[j] * du + 2.0 * pv.Rm[j] * u[j]);
             if (k) atomicAdd(&gb[(k - 1) * S + NX + j], -2.0 * pv.R[j] * du);
         }
-        if (k == N - 1) MMPC_UNROLL for (int j = 0; j < NX; ++j) gb[N * S + j] = 0.0;
+        if (k == N - 1) MMPC_UNROLL for (int j = 0; j < NX; ++j) gb[N * S + j] = node ? 2.0 * pv.Q[j] * e[j] : 0.0;
     }
     if (Hzz) {
         double* Hb = Hzz + ((size_t)b * N + k) * S * S;
@@ -426,8 +429,9 @@ __global__ void __launch_bounds__(128) nlp_eval_kernel(mmpc_problem P, int B, co
             MMPC_UNROLL for (int i = 0; i < NX; ++i) {
                 const double fa = a < NX ? fx[i * NX + a] : fu[i * NU + a - NX];
                 const double fc = c < NX ? fx[i * NX + c] : fu[i * NU + c - NX];
-                acc = fma(wq[i] * fa, fc, acc);
+                acc = fma(wqh[i] * fa, fc, acc);
             }
+            if (node && a == c && a < NX && k) acc += wq[a];  // constant block of the tracking term on x_k (x_N's block, 2 lam_f Q, is implicit)
             if (a == c && a >= NX) acc += 2.0 * lam_f * (pv.R[a - NX] + pv.Rm[a - NX]) + (k < N - 1 ? 2.0 * lam_f * pv.R[a - NX] : 0.0);
             Hb[a * S + c] = acc;
         }
@@ -592,7 +596,7 @@ struct Launch {
                                                    cudaStream_t st, int* launches) {                                    \
         if (P.integrator == MMPC_RK4 && P.is_linear) return cudaErrorNotSupported;                                      \
         /* bounds and RK4: T1, and T3 for small models (the ABI layer switches variants) */                              \
-        if (W.variant == 2 && P.bounded) return cudaErrorNotSupported;                                                  \
+        if (W.variant == 2 && (P.bounded || P.node_cost)) return cudaErrorNotSupported;                                 \
         if (W.variant == 2 && P.integrator != MMPC_EULER) return cudaErrorNotSupported;                                 \
         if (launches) ++*launches;                                                                                      \
         if (W.variant == 2) return mmpc_solve_t2_##MODEL(&P, &W, &io, st);                                              \

@@ -100,8 +100,9 @@ __device__ bool backward_sweep(const SolveCtx<M>& c, double delta, double mu, Sw
     MMPC_UNROLL for (int i = 0; i < NU * NU; ++i) Pvv[i] = 0.0;
     MMPC_UNROLL for (int i = 0; i < NX; ++i) px[i] = 0.0;
     MMPC_UNROLL for (int i = 0; i < NU; ++i) pv[i] = 0.0;
-    double wq[NX];
-    MMPC_UNROLL for (int i = 0; i < NX; ++i) wq[i] = 2.0 * c.Q[i];
+    double wq[NX], wqh[NX];
+    const bool node = c.P.node_cost != 0;  // MMPC_COST_NODE: tracking error on the decision variable x_{k+1}
+    MMPC_UNROLL for (int i = 0; i < NX; ++i) { wq[i] = 2.0 * c.Q[i]; wqh[i] = node ? 0.0 : wq[i]; }
     double du_next[NU];  // 2 R (u_{k+1} - u_k): enters the u_k stationarity residual
     MMPC_UNROLL for (int j = 0; j < NU; ++j) du_next[j] = 0.0;
     double xn[NX];
@@ -120,6 +121,12 @@ __device__ bool backward_sweep(const SolveCtx<M>& c, double delta, double mu, Sw
             xn_dres[i] = t.dres;
         }
     }
+    if (node) {  // the tracking term of x_N is the terminal value function
+        MMPC_UNROLL for (int i = 0; i < NX; ++i) {
+            Pxx[i * NX + i] += wq[i];
+            px[i] += wq[i] * (xn[i] - c.traj(N - 1, i));
+        }
+    }
     bool ok = true;
     for (int k = N - 1; k >= 0; --k) {
         double x[NX], u[NU], v[NU], r[NX], lam[NX], lam_prev[NX];
@@ -134,10 +141,10 @@ __device__ bool backward_sweep(const SolveCtx<M>& c, double delta, double mu, Sw
             v[j] = k ? c.ld(c.W.U, (k - 1) * NU + j) : c.uinit[j];
         }
         double F[NX], Fx[NX * NX], Fu[NX * NU], H[NH];
-        c.template step<RICCATI ? 2 : 1>(x, u, wq, r, lam, F, Fx, Fu, H);
+        c.template step<RICCATI ? 2 : 1>(x, u, wqh, r, lam, F, Fx, Fu, H);
         double cres[NX], qe[NX];
         MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-            const double e = F[i] - r[i];
+            const double e = (node ? xn[i] : F[i]) - r[i];
             cres[i] = F[i] - xn[i];
             qe[i] = wq[i] * e;
             nrm.fval = fma(c.Q[i] * e, e, nrm.fval);
@@ -145,7 +152,7 @@ __device__ bool backward_sweep(const SolveCtx<M>& c, double delta, double mu, Sw
             nrm.theta += fabs(cres[i]);
             nrm.lam_l1 += fabs(lam[i]);
             // stationarity w.r.t. x_{k+1}: (its own stage terms were added when it was x of stage k+1) - lam_k - zl + zu
-            if (k == N - 1) nrm.dual_inf = fmax(nrm.dual_inf, fabs(-lam[i] + xn_dres[i]));
+            if (k == N - 1) nrm.dual_inf = fmax(nrm.dual_inf, fabs((node ? qe[i] : 0.0) - lam[i] + xn_dres[i]));
         }
         // barrier terms of this stage's variables
         double sgx[NX], gpx[NX], drx[NX], sgu[NU], gpu_[NU], dru[NU];
@@ -167,16 +174,17 @@ __device__ bool backward_sweep(const SolveCtx<M>& c, double delta, double mu, Sw
         MMPC_UNROLL for (int j = 0; j < NX; ++j) {
             double a = 0.0, l = 0.0;
             MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-                a = fma(Fx[i * NX + j], qe[i], a);
+                if (!node) a = fma(Fx[i * NX + j], qe[i], a);
                 l = fma(Fx[i * NX + j], lam[i], l);
             }
+            if (node && k) a = wq[j] * (x[j] - c.traj(k - 1, j));  // x_k's own tracking term (x_0 is pinned)
             qx[j] = a + gpx[j];
             if (k) nrm.dual_inf = fmax(nrm.dual_inf, fabs(a + l - lam_prev[j] + drx[j]));
         }
         MMPC_UNROLL for (int j = 0; j < NU; ++j) {
             double a = 0.0, l = 0.0;
             MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-                a = fma(Fu[i * NU + j], qe[i], a);
+                if (!node) a = fma(Fu[i * NU + j], qe[i], a);
                 l = fma(Fu[i * NU + j], lam[i], l);
             }
             const double du = u[j] - v[j], dRu = 2.0 * c.R[j] * du;
@@ -195,9 +203,9 @@ __device__ bool backward_sweep(const SolveCtx<M>& c, double delta, double mu, Sw
                 MMPC_UNROLL for (int i = 0; i < NX; ++i) {
                     const double fa = a < NX ? Fx[i * NX + a] : Fu[i * NU + a - NX];
                     const double fd = d < NX ? Fx[i * NX + d] : Fu[i * NU + d - NX];
-                    acc = fma(wq[i] * fa, fd, acc);
+                    acc = fma(wqh[i] * fa, fd, acc);
                 }
-                if (a == d) acc += delta + (a >= NX ? 2.0 * (c.R[a - NX] + c.Rm[a - NX]) + sgu[a - NX] : sgx[a]);
+                if (a == d) acc += delta + (a >= NX ? 2.0 * (c.R[a - NX] + c.Rm[a - NX]) + sgu[a - NX] : sgx[a] + ((node && k) ? wq[a] : 0.0));
                 H[tri(a, d, S)] = acc;
             }
             double y[NX], yv[NU];
@@ -389,7 +397,8 @@ __device__ void forward_sweep(const SolveCtx<M>& c, double mu, FwdOut& o) {
             dxn[i] = a;
             c.st(c.W.DX, (k + 1) * NX + i, a);
             // directional derivative of e'Qe: 2 Q e . (Fx dx + Fu du) = 2 Q e . (dxn - c)
-            o.gradf_d = fma(wq[i] * (F[i] - r[i]), a - (F[i] - xn[i]), o.gradf_d);
+            if (c.P.node_cost) o.gradf_d = fma(wq[i] * (xn[i] - r[i]), a, o.gradf_d);  // 2 Q (x_{k+1} - r_k) . dx_{k+1}
+            else o.gradf_d = fma(wq[i] * (F[i] - r[i]), a - (F[i] - xn[i]), o.gradf_d);
         }
         MMPC_UNROLL for (int j = 0; j < NU; ++j) {
             o.gradf_d = fma(2.0 * c.R[j] * (u[j] - v[j]), du[j] - dv[j], o.gradf_d);
@@ -430,7 +439,7 @@ __device__ void forward_sweep(const SolveCtx<M>& c, double mu, FwdOut& o) {
             MMPC_UNROLL for (int j = 0; j < NU; ++j) ut[j] = u[j] + du[j];
             c.template step<0>(xt, ut, nullptr, nullptr, nullptr, Ft, nullptr, nullptr, nullptr);
             MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-                const double e = Ft[i] - r[i];
+                const double e = (c.P.node_cost ? xn[i] + dxn[i] : Ft[i]) - r[i];
                 o.f1 = fma(c.Q[i] * e, e, o.f1);
                 o.theta1 += fabs(Ft[i] - (xn[i] + dxn[i]));
             }
@@ -463,7 +472,7 @@ __device__ void trial_eval(const SolveCtx<M>& c, double alpha, double& f1, doubl
         MMPC_UNROLL for (int i = 0; i < NX; ++i) xn[i] = fma(alpha, c.ld(c.W.DX, (k + 1) * NX + i), c.ld(c.W.X, (k + 1) * NX + i));
         c.template step<0>(x, u, nullptr, nullptr, nullptr, F, nullptr, nullptr, nullptr);
         MMPC_UNROLL for (int i = 0; i < NX; ++i) {
-            const double e = F[i] - c.traj(k, i);
+            const double e = (c.P.node_cost ? xn[i] : F[i]) - c.traj(k, i);
             f1 = fma(c.Q[i] * e, e, f1);
             theta1 += fabs(F[i] - xn[i]);
             x[i] = xn[i];

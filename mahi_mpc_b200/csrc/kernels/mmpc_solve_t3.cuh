@@ -142,7 +142,7 @@ template <class M, int I_, int MODE_ = 0>
 struct T3Ctx : T3CtxBounds<M, ((MODE_ >> 1) & 1) != 0> {
     static constexpr int NX = M::NX, NU = M::NU, S = NX + NU, I = I_;
     double h;                     // step size; is_linear / substeps: copies of the problem constants the sweeps need
-    int is_linear, substeps, gauss_newton;
+    int is_linear, substeps, gauss_newton, node_cost;
     int N;
     double *V, *LAM, *DV, *LAMN;  // this thread's instance inside the tile arrays: element e lives at [e * I]
     double* LINp;                 // linearisation data of the instance (AoS)
@@ -220,22 +220,31 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I, C::MODE>& c, i
         }
     }
     double F[NX], Fx[NX * NX], Fu[NX * NU], H[NH];
-    c.template step<2>(x, u, wq, r, lam, F, Fx, Fu, H);
+    // MMPC_COST_NODE: the tracking error sits on the decision variable x_{k+1}; node k then carries x_k's own term
+    // 2 Q (x_k - r_{k-1}) (gradient) and 2 Q (Hessian diagonal) for k >= 1, x_N's term is the terminal value function
+    // (t3_backward), the Hessian weights are lam alone and there is no Gauss-Newton block
+    const bool nc = c.node_cost != 0;
+    double wqh[NX], gxn[NX];
+    MMPC_UNROLL for (int a = 0; a < NX; ++a) {
+        wqh[a] = nc ? 0.0 : wq[a];
+        gxn[a] = (nc && k) ? wq[a] * (x[a] - c.traj[(size_t)(k - 1) * NX + a]) : 0.0;
+    }
+    c.template step<2>(x, u, wqh, r, lam, F, Fx, Fu, H);
     double* const recp = rec + (size_t)j * C::RB * I + i;
     double* const fgp = fg_tile + (size_t)k * C::FG_NS * I + i;
 #define T3_REC(f) recp[(f) * I]
 #define T3_FG(f, v) T3_ST(&fgp[(f) * I], (v))
     double qe[NX], dual = 0.0, prim = 0.0, theta = 0.0, fval = 0.0, lam1 = 0.0;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) {
-        const double e = F[a] - r[a], cr = F[a] - xn[a];
-        qe[a] = wq[a] * e;
+        const double e = (nc ? xn[a] : F[a]) - r[a], cr = F[a] - xn[a];
+        qe[a] = wqh[a] * e;  // pulled back through Fx, Fu below (shooting cost only)
         fval = fma(c.Q[a] * e, e, fval);
         prim = fmax(prim, fabs(cr));
         theta += fabs(cr);
         lam1 += fabs(lam[a]);
         T3_REC(C::RB_C + a) = cr;
         T3_FG(C::FG_C + a, cr);
-        if (k == N - 1) dual = fmax(dual, fabs(lam[a]));  // stationarity w.r.t. x_N is -lam_{N-1}
+        if (k == N - 1) dual = fmax(dual, fabs((nc ? wq[a] * e : 0.0) - lam[a]));  // stationarity w.r.t. x_N: (2 Q e_N) - lam_{N-1}
     }
     MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) if (T3_FXNZ(a / NX, a % NX)) { T3_REC(C::RB_FX + T3_FXSLOT(a)) = Fx[a]; T3_FG(C::FG_FX + T3_FXSLOT(a), Fx[a]); }
     MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) if (T3_FUNZ(a / NU, a % NU)) { T3_REC(C::RB_FU + T3_FUSLOT(a)) = Fu[a]; T3_FG(C::FG_FU + T3_FUSLOT(a), Fu[a]); }
@@ -245,6 +254,7 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I, C::MODE>& c, i
             g = fma(Fx[q * NX + a], qe[q], g);
             l = fma(Fx[q * NX + a], lam[q], l);
         }
+        g += gxn[a];
         T3_REC(C::RB_Q + a) = g;
         T3_FG(C::FG_Q + a, g);
         if (k) dual = fmax(dual, fabs(g + l - lam_prev[a]));
@@ -272,10 +282,10 @@ __device__ __forceinline__ void t3_eval_node(const T3Ctx<M, C::I, C::MODE>& c, i
             if (nzp && nzd) {
                 const double fa = p < NX ? Fx[q * NX + p] : Fu[q * NU + p - NX];
                 const double fd = d < NX ? Fx[q * NX + d] : Fu[q * NU + d - NX];
-                acc = fma(wq[q] * fa, fd, acc);
+                acc = fma(wqh[q] * fa, fd, acc);
             }
         }
-        if (p == d) acc += delta + (p >= NX ? 2.0 * (c.R[p - NX] + c.Rm[p - NX]) : 0.0);
+        if (p == d) acc += delta + (p >= NX ? 2.0 * (c.R[p - NX] + c.Rm[p - NX]) : ((nc && k) ? wq[p] : 0.0));
         if constexpr (C::BD != 0) {
             if (p == d && p >= NX) acc += sgu[p - NX];
         }
@@ -502,6 +512,12 @@ __device__ __noinline__ bool t3_backward(const T3Ctx<M, C::I, C::MODE>& cin, dou
         MMPC_UNROLL for (int a = 0; a < NU * NU; ++a) V.Pvv[a] = 0.0;
         MMPC_UNROLL for (int a = 0; a < NX; ++a) V.px[a] = 0.0;
         MMPC_UNROLL for (int a = 0; a < NU; ++a) V.pv[a] = 0.0;
+        if (c.node_cost && tid < I) {  // MMPC_COST_NODE: x_N's tracking term is the terminal value function
+            MMPC_UNROLL for (int a = 0; a < NX; ++a) {
+                V.Pxx[a * NX + a] = 2.0 * c.Q[a];
+                V.px[a] = 2.0 * c.Q[a] * (c.V[((size_t)N * C::S + a) * I] - c.traj[(size_t)(N - 1) * NX + a]);
+            }
+        }
         double R[NU];
         MMPC_UNROLL for (int a = 0; a < NU; ++a) R[a] = c.R[a];
         for (int step = nch; step >= 0; --step) {
@@ -585,16 +601,19 @@ __device__ __noinline__ void t3_residuals(const T3Ctx<M, C::I, C::MODE>& cin, do
             double F[NX], Fx[NX * NX], Fu[NX * NU], qe[NX];
             c.template step<1>(x, u, nullptr, nullptr, nullptr, F, Fx, Fu, nullptr);
             SweepNorms own{};  // x_k's terms are accumulated by node k-1 (as its x_{k+1}); here only its -zl + zu is needed
+            const bool nc = c.node_cost != 0;  // MMPC_COST_NODE: see t3_eval_node
+            double qxn[NX];
             MMPC_UNROLL for (int a = 0; a < NX; ++a) {
-                const double e = F[a] - r[a], cr = F[a] - xn[a];
-                qe[a] = 2.0 * c.Q[a] * e;
+                const double e = (nc ? xn[a] : F[a]) - r[a], cr = F[a] - xn[a];
+                qe[a] = nc ? 0.0 : 2.0 * c.Q[a] * e;
+                qxn[a] = nc ? 2.0 * c.Q[a] * e : 0.0;
                 n.fval = fma(c.Q[a] * e, e, n.fval);
                 n.prim_inf = fmax(n.prim_inf, fabs(cr));
                 n.theta += fabs(cr);
                 n.lam_l1 += fabs(lam[a]);
                 double dres_n = 0.0;
                 if constexpr (C::BD != 0) { dres_n = bound_term(xn[a], c.x_min[a], c.x_max[a], zln[a], zun[a], 0.0, n).dres; }
-                if (k == N - 1) n.dual_inf = fmax(n.dual_inf, C::BD ? fabs(-lam[a] + dres_n) : fabs(lam[a]));  // stationarity w.r.t. x_N
+                if (k == N - 1) n.dual_inf = fmax(n.dual_inf, C::BD ? fabs(qxn[a] - lam[a] + dres_n) : fabs(qxn[a] - lam[a]));  // stationarity w.r.t. x_N
             }
             MMPC_UNROLL for (int a = 0; a < NX; ++a) {
                 double g = 0.0, l = 0.0;
@@ -602,6 +621,7 @@ __device__ __noinline__ void t3_residuals(const T3Ctx<M, C::I, C::MODE>& cin, do
                     g = fma(Fx[q * NX + a], qe[q], g);
                     l = fma(Fx[q * NX + a], lam[q], l);
                 }
+                if (nc && k) g += 2.0 * c.Q[a] * (x[a] - c.traj[(size_t)(k - 1) * NX + a]);
                 if (k) {
                     if constexpr (C::BD != 0) {
                         const BoundTerm tx = bound_term(x[a], c.x_min[a], c.x_max[a], zlx[a], zux[a], 0.0, own);
@@ -718,7 +738,7 @@ __device__ __forceinline__ void t3_trial_node(const T3Ctx<M, C::I, C::MODE>& c, 
     if (!(C::BD && bd.full)) {
         c.template step<0>(x, u, nullptr, nullptr, nullptr, F, nullptr, nullptr, nullptr);
         MMPC_UNROLL for (int a = 0; a < NX; ++a) {
-            const double e = F[a] - r[a];
+            const double e = (c.node_cost ? xn[a] : F[a]) - r[a];
             f1 = fma(c.Q[a] * e, e, f1);
             th1 += fabs(F[a] - xn[a]);
         }
@@ -955,7 +975,7 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
 
     T3Ctx<M, I, C::MODE> c;
     c.N = N;
-    c.h = P.h; c.is_linear = P.is_linear; c.substeps = P.substeps; c.gauss_newton = P.gauss_newton;
+    c.h = P.h; c.is_linear = P.is_linear; c.substeps = P.substeps; c.gauss_newton = P.gauss_newton; c.node_cost = P.node_cost;
     // the iterate lives tile-wise, [element][instance]: every access of a warp is a run of full sectors whatever I is
     c.V = W.V2 + (size_t)tile * I * NV + i; c.LAM = W.LAM2 + (size_t)tile * I * Mc + i;
     c.DV = W.DV2 + (size_t)tile * I * NV + i; c.LAMN = W.LAMN2 + (size_t)tile * I * Mc + i;
@@ -1319,6 +1339,7 @@ struct LaunchT3 {
     // The tile width fixes the layout of the persistent iterate, so the choice depends only on the batch size of the
     // handle.  kernel_variant = 3 + 256*k forces configuration k.
     static cudaError_t run(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
+        if (P.node_cost) return cudaErrorNotSupported;  // MMPC_COST_NODE: T4 / T1 (T3's forward sweep has no terminal objective term)
         const int forced = io.variant >> 8;
         const int cfg = forced ? forced : (W.B > 8 * 148 ? 2 : 1);
         if (P.bounded) {

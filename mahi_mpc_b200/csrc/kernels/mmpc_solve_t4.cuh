@@ -185,6 +185,10 @@ __device__ __noinline__ void t4_forward(const T3Ctx<M, C::I, C::MODE>& cin, doub
             gsum = fma(pb[(C::RP_Q + NX + a) * I], dv[a], gsum);
             gsum = fma(pb[(C::RP_Q + S + a) * I], du[a], gsum);
         }
+        if (c.node_cost && k == N - 1) {  // MMPC_COST_NODE: x_N's tracking term is in no node record (terminal value function)
+            MMPC_UNROLL for (int a = 0; a < NX; ++a)
+                gsum = fma(2.0 * c.Q[a] * (z[(S + a) * I] - c.traj[(size_t)k * NX + a]), dxn[a], gsum);
+        }
         // lam_k+ = (P_{k+1} (dx_{k+1}, du_k) + p_{k+1})_x
         MMPC_UNROLL for (int a = 0; a < NX; ++a) {
             double t = pb[(C::RP_P + C::PG_X + a) * I];
@@ -398,7 +402,7 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
 
     T3Ctx<M, I, C::MODE> c;
     c.N = N;
-    c.h = P.h; c.is_linear = P.is_linear; c.substeps = P.substeps; c.gauss_newton = P.gauss_newton;
+    c.h = P.h; c.is_linear = P.is_linear; c.substeps = P.substeps; c.gauss_newton = P.gauss_newton; c.node_cost = P.node_cost;
     // the iterate lives tile-wise, [element][instance] (T3's layout)
     c.V = W.V2 + (size_t)tile * I * NV + i; c.LAM = W.LAM2 + (size_t)tile * I * Mc + i;
     c.DV = W.DV2 + (size_t)tile * I * NV + i; c.LAMN = W.LAMN2 + (size_t)tile * I * Mc + i;

@@ -6,7 +6,7 @@
 
 #define MMPC_MAXNX 16
 #define MMPC_MAXNU 8
-#define MMPC_VTABLE_VERSION 7
+#define MMPC_VTABLE_VERSION 8
 
 struct mmpc_stats;  // public struct (include/mahi_mpc_b200.h)
 
@@ -19,6 +19,7 @@ struct mmpc_problem {
     double h;        // step_size in seconds
     int bounded;     // any finite bound present
     int gauss_newton;  // RK4 shooting only: drop the second derivatives of the integrator from the Lagrangian Hessian
+    int node_cost;     // tracking error on the decision variable x_{k+1} instead of F(x_k, u_k) (MMPC_COST_NODE)
     double x_min[MMPC_MAXNX], x_max[MMPC_MAXNX], u_min[MMPC_MAXNU], u_max[MMPC_MAXNU];
 };
 

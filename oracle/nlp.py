@@ -39,6 +39,10 @@ class Problem:
     is_linear: bool = False
     integrator: str = "euler"  # "euler" (library parity) | "rk4"
     hessian: str = "exact"     # "exact" | "gauss_newton" (RK4 only: drop the integrator's second derivatives)
+    # "shooting": tracking error on F(x_k, u_k) - r_k, the C++ library's objective (ModelGenerator.cpp:207-214);
+    # "node": on the decision variable, x_{k+1} - r_k, the MATLAB prototypes' (workingMPC_8_30_21.m:90-106: the error of x(:,k)
+    # against the reference at its own time, with Q <- 1000 Q, no du term, Rm <- R there; x_0 is pinned, its term is a constant)
+    cost: str = "shooting"
     substeps: int = 1
 
     def __post_init__(self):
@@ -192,7 +196,7 @@ class Problem:
     def nlp_f(self, V, p):
         X, U = self.split_V(V)
         P = self.split_p(p)
-        e = self.step(X[:-1], U, P) - P["r"]
+        e = (X[1:] if self.cost == "node" else self.step(X[:-1], U, P)) - P["r"]
         dU = U - np.vstack([P["u_init"][None], U[:-1]])
         return float((e * e * P["Q"]).sum() + (dU * dU * P["R"]).sum() + (U * U * P["Rm"]).sum())
 
@@ -200,9 +204,16 @@ class Problem:
         nx, N = self.nx, self.N
         X, U = self.split_V(V)
         P = self.split_p(p)
+        dU = U - np.vstack([P["u_init"][None], U[:-1]])
+        if self.cost == "node":
+            e = X[1:] - P["r"]
+            gx = np.vstack([np.zeros((1, nx)), 2.0 * P["Q"] * e])  # d/dx_{k+1}, k = 0..N-1; x_0 carries none
+            gu = 2 * P["R"] * dU + 2 * P["Rm"] * U
+            gu[:-1] -= 2 * P["R"] * dU[1:]
+            f = float((e * e * P["Q"]).sum() + (dU * dU * P["R"]).sum() + (U * U * P["Rm"]).sum())
+            return f, self.join_V(gx, gu)
         F, Fx, Fu = self.step_jac(X[:-1], U, P)
         e = F - P["r"]
-        dU = U - np.vstack([P["u_init"][None], U[:-1]])
         qe = 2.0 * P["Q"] * e
         gx = np.einsum("kij,ki->kj", Fx, qe)
         gu = np.einsum("kij,ki->kj", Fu, qe) + 2 * P["R"] * dU + 2 * P["Rm"] * U
@@ -233,14 +244,18 @@ class Problem:
         F, Fx, Fu = self.step_jac(X[:-1], U, P)
         e = F - P["r"]
         lam = np.asarray(lam_g, float).reshape(N, nx)
-        W = 2.0 * lam_f * P["Q"] * e + lam
+        node = self.cost == "node"
+        W = lam if node else 2.0 * lam_f * P["Q"] * e + lam
         H = np.zeros((self.NV, self.NV))
         Hc = self.step_hess(X[:-1], U, P, W)
         Fz = np.concatenate([Fx, Fu], axis=2)  # (N,nx,s)
         for k in range(N):
             c0 = k * s
-            blk = 2.0 * lam_f * (Fz[k].T * P["Q"]) @ Fz[k] + Hc[k]
+            blk = Hc[k] if node else 2.0 * lam_f * (Fz[k].T * P["Q"]) @ Fz[k] + Hc[k]
             H[c0:c0 + s, c0:c0 + s] += blk
+            if node:  # the tracking term sits on the decision variable x_{k+1}: a constant diagonal block
+                ix = np.arange((k + 1) * s, (k + 1) * s + nx)
+                H[ix, ix] += 2.0 * lam_f * P["Q"]
             iu = np.arange(c0 + nx, c0 + s)
             H[iu, iu] += 2 * lam_f * (P["R"] + P["Rm"])
             if k < N - 1:

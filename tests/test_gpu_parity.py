@@ -685,3 +685,77 @@ def test_small_batch_packed_staging_and_stats_jsonl(api, coracle, tmp_path):
     subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     lines = [json.loads(l) for l in out.read_text().splitlines()]
     assert len(lines) == 2 and lines[0]["batch"] == 5 and lines[0]["converged"] == 5 and lines[0]["kernel_ms"] > 0 and lines[0]["N"] == 25
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# MMPC_COST_NODE: the MATLAB prototypes' objective (workingMPC_8_30_21.m:90-106) -- tracking error on the decision
+# variable x_{k+1} instead of F(x_k, u_k); with RK4 x 4, Q <- 1000 Q, R <- 0, Rm <- R this is the prototypes' NLP.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("proto", [False, True])
+def test_node_cost_nlp_eval_vs_oracle(api, proto):
+    N, B = (10, 3) if proto else (25, 2)
+    h = 0.1 if proto else 0.002
+    kw = dict(integrator="rk4", substeps=4) if proto else {}
+    P = nlp.Problem(N=N, h=h, cost="node", **kw)
+    Q, R, Rm = (np.full(4, 1000.0), np.zeros(2), np.ones(2)) if proto else nlp.default_weights(4, 2)
+    x0, up, traj = nlp.synthetic_batch(4, 2, N, h, B)
+    p = np.stack([P.pack_p(traj[b], Q, R, Rm, up[b]) for b in range(B)])
+    m = api.Model("double_pendulum", N=N, step_size_us=int(round(h * 1e6)))
+    rng = np.random.default_rng(21)
+    V = rng.uniform(-0.5, 0.5, (B, P.NV)); lam = rng.uniform(-1, 1, (B, P.M))
+    o = api.default_options(cost=api.COST_NODE, **(dict(integrator=api.RK4, substeps=4) if proto else {}))
+    out = m.nlp_eval(V, p, lam, opts=o)
+    for b in range(B):
+        f, gf = P.nlp_grad_f(V[b], p[b])
+        H = P.nlp_hess_l(V[b], p[b], 1.0, lam[b])
+        assert abs(out["f"][b] - f) <= EVAL_RTOL * abs(f) and rel(out["g"][b], P.nlp_g(V[b], p[b])) < EVAL_RTOL
+        assert np.abs(out["grad_f"][b] - gf).max() <= 1e-11 * np.abs(gf).max()
+        for k in range(N):
+            blk = H[k * 6:(k + 1) * 6, k * 6:(k + 1) * 6]
+            assert np.abs(out["Hzz"][b, k] - blk).max() <= 1e-10 * max(1.0, np.abs(blk).max()), (b, k)
+        assert np.allclose(np.diag(H[N * 6:, N * 6:]), 2 * Q)  # the implicit constant block of x_N
+
+
+@pytest.mark.parametrize("variant", [0, 1, 4 + 256 * 1, 4 + 256 * 2, 4 + 256 * 3])
+@pytest.mark.parametrize("proto", [False, True])
+def test_node_cost_solve_vs_oracle(api, variant, proto):
+    N, B = (10, 5) if proto else (25, 9)
+    h = 0.1 if proto else 0.002
+    kw = dict(integrator="rk4", substeps=4) if proto else {}
+    P = nlp.Problem(N=N, h=h, cost="node", **kw)
+    Q, R, Rm = (np.full(4, 1000.0), np.zeros(2), np.ones(2)) if proto else nlp.default_weights(4, 2)
+    x0, up, traj = nlp.synthetic_batch(4, 2, N, h, B)
+    if proto:
+        x0 = x0 * 0.0  # the prototypes start at rest
+    p = np.stack([P.pack_p(traj[b], Q, R, Rm, up[b]) for b in range(B)])
+    ref = [nlp.solve(P, x0[b], p[b], tol=1e-10, max_iter=200) for b in range(B)]
+    assert all(r.status == 0 for r in ref)
+    m = api.Model("double_pendulum", N=N, step_size_us=int(round(h * 1e6)))
+    s = api.Solver(m, B, tol=1e-9, warm_start=0, kernel_variant=variant, cost=api.COST_NODE,
+                   **(dict(integrator=api.RK4, substeps=4) if proto else {}))
+    s.set_weights(Q, R, Rm)
+    V, lam, st = s.solve(x0, up, traj)
+    assert (st["status"] == 0).all(), st
+    for b, r in enumerate(ref):
+        assert np.abs(V[b] - r.V).max() < U_ATOL and abs(st["objective"][b] - r.f) <= OBJ_RTOL * max(1.0, abs(r.f)), (variant, b)
+        assert abs(int(st["iterations"][b]) - r.iters) <= 1
+        assert np.abs(lam[b] - r.lam_g).max() <= 1e-6 * max(1.0, np.abs(r.lam_g).max())
+
+
+def test_node_cost_with_control_limits_uses_t1(api):
+    N, B = 25, 6
+    P = nlp.Problem(N=N, cost="node")
+    Q, R, Rm = nlp.default_weights(4, 2)
+    x0, up, traj = nlp.synthetic_batch(4, 2, N, P.h, B)
+    p = np.stack([P.pack_p(traj[b], Q, R, Rm, up[b]) for b in range(B)])
+    ub = 2.0
+    m = api.Model("double_pendulum", N=N)
+    s = api.Solver(m, B, tol=1e-8, warm_start=0, cost=api.COST_NODE)
+    s.set_weights(Q, R, Rm)
+    s.set_bounds(u_min=[-ub, -ub], u_max=[ub, ub])
+    V, lam, st = s.solve(x0, up, traj)
+    assert (st["status"] == 0).all()
+    for b in range(B):
+        lb_, ub_ = nlp.bounds_vectors(P, x0[b], u_min=[-ub] * 2, u_max=[ub] * 2)
+        r = nlp.solve(P, x0[b], p[b], lb=lb_, ub=ub_, tol=1e-9, max_iter=300)
+        assert r.status == 0 and np.abs(V[b] - r.V).max() < U_ATOL

@@ -183,3 +183,31 @@ def test_rk4_hessian_oracle_vs_mpmath_golden():
         # Gauss-Newton option: no integrator second derivatives
         Pg = nlp.Problem(N=2, h=c["h"], integrator="rk4", substeps=c["substeps"], hessian="gauss_newton")
         assert not Pg.step_hess(x, u, {}, w).any()
+
+
+def test_node_cost_oracle_derivatives_by_finite_differences():
+    """oracle/nlp.py with cost = "node" (the MATLAB prototypes' objective, workingMPC_8_30_21.m:90-106): gradient and
+    Lagrangian Hessian against central finite differences, Euler and RK4 x 2; a solve converges to a KKT point."""
+    for integ, sub in (("euler", 1), ("rk4", 2)):
+        P = nlp.Problem(N=6, h=0.05, integrator=integ, substeps=sub, cost="node")
+        Q, R, Rm = nlp.default_weights(4, 2)
+        x0, up, traj = nlp.synthetic_batch(4, 2, 6, 0.05, 1)
+        p = P.pack_p(traj[0], Q, R, Rm, up[0])
+        rng = np.random.default_rng(0)
+        V = rng.uniform(-.5, .5, P.NV); lam = rng.uniform(-1, 1, P.M)
+        f, g = P.nlp_grad_f(V, p)
+        assert abs(f - P.nlp_f(V, p)) < 1e-12 * abs(f)
+        eps = 1e-6
+
+        def grad_l(Vq):
+            _, gq = P.nlp_grad_f(Vq, p)
+            _, J = P.nlp_jac_g(Vq, p)
+            return gq + J.T @ lam
+        H = P.nlp_hess_l(V, p, 1.0, lam)
+        for i in range(P.NV):
+            Vp, Vm = V.copy(), V.copy()
+            Vp[i] += eps; Vm[i] -= eps
+            assert abs((P.nlp_f(Vp, p) - P.nlp_f(Vm, p)) / (2 * eps) - g[i]) < 1e-6
+            assert np.abs((grad_l(Vp) - grad_l(Vm)) / (2 * eps) - H[:, i]).max() < 1e-6
+        r = nlp.solve(P, x0[0], p, tol=1e-10, max_iter=100)
+        assert r.status == 0 and r.kkt_error < 1e-10
