@@ -139,20 +139,28 @@ __device__ __noinline__ void t4_forward(const T3Ctx<M, C::I, C::MODE>& cin, doub
     constexpr unsigned B_CHAIN = C::REC_C * I * 8, B_POST = C::REC_P * I * 8;
     const double* rec_tile = fg_tile;  // FG | KG | PG are ONE record per node here (kg_tile, pg_tile point into it)
     (void)kg_tile; (void)pg_tile;
-    // bulk copies of step ch: the chain parts of chunk ch+1 and the post parts of chunk ch, one copy per worker thread w < 2 CF
-    // (a single thread needs ~90 cycles per copy to issue them); worker 0 announces the bytes.  A copy may complete before the
-    // announcement: the phase cannot end before the announcing thread's arrival.
+    // bulk copies of step ch: the chain parts of chunk ch+1 and the post parts of chunk ch, one copy per lane (a single thread
+    // needs ~90 cycles per copy to issue them back to back); the first lane announces the bytes.  A copy may complete before the
+    // announcement: the phase cannot end before the announcing thread's arrival.  The issuing lanes are the workers of the LAST
+    // node slot when that slot has no node to post-process (CF < CB: it is beyond the forward chunk), so that issuing
+    // (~0.9 k cycles per step) is not in front of any thread's post-processing.
+#ifdef MMPC_T4_ISSUE_FIRST_WARP
+    constexpr bool SPARE_SLOT = false;
+#else
+    constexpr bool SPARE_SLOT = C::CB - 1 >= C::CF && I >= 2 * C::CF;
+#endif
+    const int wl = SPARE_SLOT ? (wj == C::CB - 1 ? wi : -1) : w;  // lane of the issuing group (-1: not an issuer)
     auto issue_loads = [&](int ch_chain, int ch_post) {
         const int knc = ch_chain < nch ? min(C::CF, N - ch_chain * C::CF) : 0, knp = ch_post >= 0 ? min(C::CF, N - ch_post * C::CF) : 0;
-        if (w == 0) {
+        if (wl == 0) {
             if (knc) t4_mbar_arrive_expect_tx(&bars[ch_chain & 1], (unsigned)knc * B_CHAIN);
             if (knp) t4_mbar_arrive_expect_tx(&bars[2 + (ch_post & 1)], (unsigned)knp * B_POST);
         }
-        if (w < knc) {
-            const int k = ch_chain * C::CF + w;
-            t4_bulk_load(smem + C::SM_REC + (ch_chain & 1) * C::BUF + C::FW_CHAIN + (size_t)w * C::RC * I, rec_tile + (size_t)k * C::REC * I, B_CHAIN, &bars[ch_chain & 1]);
-        } else if (w >= C::CF && w - C::CF < knp) {
-            const int s = w - C::CF, k = ch_post * C::CF + s;
+        if (wl >= 0 && wl < knc) {
+            const int k = ch_chain * C::CF + wl;
+            t4_bulk_load(smem + C::SM_REC + (ch_chain & 1) * C::BUF + C::FW_CHAIN + (size_t)wl * C::RC * I, rec_tile + (size_t)k * C::REC * I, B_CHAIN, &bars[ch_chain & 1]);
+        } else if (wl >= C::CF && wl - C::CF < knp) {
+            const int s = wl - C::CF, k = ch_post * C::CF + s;
             t4_bulk_load(smem + C::SM_REC + (ch_post & 1) * C::BUF + C::FW_POST + (size_t)s * C::RP * I, rec_tile + ((size_t)k * C::REC + C::REC_C) * I, B_POST,
                          &bars[2 + (ch_post & 1)]);
         }
