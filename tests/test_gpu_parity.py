@@ -759,3 +759,21 @@ def test_node_cost_with_control_limits_uses_t1(api):
         lb_, ub_ = nlp.bounds_vectors(P, x0[b], u_min=[-ub] * 2, u_max=[ub] * 2)
         r = nlp.solve(P, x0[b], p[b], lb=lb_, ub=ub_, tol=1e-9, max_iter=300)
         assert r.status == 0 and np.abs(V[b] - r.V).max() < U_ATOL
+
+
+@pytest.mark.parametrize("N", [10, 100, 200])
+def test_horizon_sweep_full_batch_vs_oracle(api, coracle, N):
+    """BASELINE config 4 (horizon sweep at batch 4096) as bench.py's `other_configs.horizon_sweep` runs it: ALL 4096 instances of
+    every horizon against the oracle at the reference's tol = 1e-5 (N = 50 is test_solve_headline_config_vs_oracle)."""
+    B = 4096
+    P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B)
+    Vo, lamo, sto, bad = coracle.solve_batch("double_pendulum", N, P.h, False, x0, p, tol=1e-5)
+    assert bad == 0
+    m = api.Model("double_pendulum", N=N)
+    s = api.Solver(m, B, warm_start=0)
+    s.set_weights(Q, R, Rm)
+    V, lam, st = s.solve(x0, up, traj)
+    assert (st["status"] == 0).all() and (st["kkt_error"] <= 1e-5).all()
+    assert np.abs(V - Vo).max() < U_ATOL
+    assert (np.abs(st["objective"] - sto["f"]) <= OBJ_RTOL * np.abs(sto["f"])).all()
+    assert (st["iterations"] == sto["iters"]).mean() > 0.99, np.bincount(np.abs(st["iterations"] - sto["iters"]))
