@@ -120,3 +120,15 @@ def test_facade_threaded_and_batched(generated_model, examples, tmp_path):
                     "-lmahi_mpc_b200", "-Wl,-rpath," + lib, "-ldl"], check=True)
     r = subprocess.run([str(exe)], cwd=generated_model, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "FACADE-THREADED-OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_prototype_closed_loop_example(examples):
+    """examples/ex_prototype_mpc.cpp: the MATLAB prototype's closed loop (workingMPC_8_30_21.m: RK4 x 4, exact Hessian, objective on
+    the decision variables with weight 1000) through the C ABI -- every cycle converges and the loop tracks the reference."""
+    import re
+    r = subprocess.run([os.path.join(examples, "ex_prototype_mpc"), "40"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "status" not in r.stderr, r.stdout[-2000:] + r.stderr[-2000:]
+    m = re.search(r"mean Newton iterations ([0-9.]+), max \|qA - reference\| after the first second ([0-9.e+-]+) rad", r.stdout)
+    assert m, r.stdout[-1000:]
+    assert float(m.group(1)) < 12 and float(m.group(2)) < 0.5, r.stdout[-1000:]  # 1000 e^2 against u^2 with |u| ~ 20 Nm: ~0.3 rad
