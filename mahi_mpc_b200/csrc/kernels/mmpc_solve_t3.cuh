@@ -8,7 +8,7 @@
 //   * worker warps (threads 32..): thread (i, j) evaluates node k0+j of instance i for a chunk of C nodes (F, dF/dx,
 //     dF/du, Lagrangian stage Hessian, residual norms; in the forward sweep the merit terms of the trial step and the
 //     cp.async staging of the next chunk) and leaves a record in shared memory, field-major with the instance index
-//     fastest so every access is bank-conflict free;
+//     fastest so the lanes of a warp read / write consecutive 8-byte words (two wavefronts per access);
 //   * warp 0: lane i runs T1's register-resident Riccati recursion (backward) and the linear rollout (forward) of
 //     instance i from those records -- no exchange, no redundant work; gains and value-function blocks go to global
 //     memory tile-wise ([node][field][instance]) so the lanes write full 256-byte lines and the forward sweep stages
