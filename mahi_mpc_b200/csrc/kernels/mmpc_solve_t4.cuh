@@ -18,8 +18,7 @@
 //     each, straight from global memory: new multipliers lam_k = (P_{k+1} (dx_{k+1}, du_k) + p_{k+1})_x, directional
 //     derivative of the objective, the step itself (z += dz) and the multiplier hand-over.  No separate pass over the
 //     iterate, no merit evaluation, no value-function rows in shared memory.
-//   * tile widths 8 (64 threads, 4 CTAs / SM: small batches), 28 (147 CTAs at B = 4096: every SM of a B200 has a tile)
-//     and 32 (larger batches).
+//   * tile widths 4 (64 threads, 8 node slots per instance: batches up to 1184) and 32 (larger batches).
 // Backward sweep, residual sweep and merit pass are T3's (mmpc_solve_t3.cuh).  Euler / linearised / RK4 shooting, no
 // finite bounds (those stay on T3 / T1).  Replaces IPOPT+MUMPS at ModelControl.cpp:159.
 #pragma once
@@ -633,20 +632,25 @@ struct LaunchT4 {
         return cudaGetLastError();
     }
     // Tile width from the batch of the handle (mmpc_t4_tile_width; it fixes the layout of the persistent iterate):
-    //   8 x 4 x 4    64 threads, 4 CTAs / SM   B <= 8 * 148: lowest latency while there is at most one narrow tile per SM
-    //  32 x 7 x 7   256 threads, 1 CTA / SM    beyond: full serial warps, 256-byte rows (whole L2 lines: see the discards)
-    //  28 x 8 x 8   256 threads, 1 CTA / SM    on request only: 147 CTAs at B = 4096 (every SM has a tile), but the serial warp
-    //               then shares its SM sub-partition with a full worker warp: 0.377 vs 0.352 ms
-    // kernel_variant = 4 + 256*k forces configuration k (1: 8, 2: 28, 3: 32).  Measured at B = 4096, N = 50 (profiles/r2_t4_configs.txt).
+    //   4 x 8 x 8    64 threads (warp 0 + one worker warp: 8 node slots per instance), B <= 8 * 148: the latency configuration --
+    //               the backward sweep is bound by the recursion, not by evaluation rounds (N = 50: 7 rounds instead of 13)
+    //  32 x 7 x 5   256 threads, 1 CTA / SM    beyond: full serial warps, 256-byte rows (whole L2 lines: see the discards)
+    //   8 x 4 x 4 and 28 x 8 x 6   on request only (tests of other tile shapes; 28: 147 CTAs at B = 4096, but the serial warp then
+    //               shares its SM sub-partition with a full worker warp: 0.377 vs 0.352 ms)
+    // kernel_variant = 4 + 256*k forces configuration k (1: 8, 2: 28, 3: 32, 4: 4).  Measured at N = 50 (profiles/r2_t4_configs.txt):
+    //   B = 4 / 32 / 296 / 592 / 1184 / 2368:  4 x 8 x 8: 0.190 / 0.212 / 0.225 / 0.224 / 0.232 / 0.342 ms,  8 x 4 x 4: 0.218 / 0.250 /
+    //   0.251 / 0.266 / 0.268 / 0.302 ms.
     static cudaError_t run(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         if (P.bounded) return cudaErrorNotSupported;
         if constexpr (M::NX + 2 * M::NU <= 8) {
             const int I = mmpc_t4_tile_width(W.B, io.variant >> 8);
             if (P.integrator == MMPC_RK4 && !P.is_linear) {
+                if (I == 4) return go<4, 8, 5, 1>(P, W, io, st);
                 if (I == 8) return go<8, 4, 4, 1>(P, W, io, st);
                 if (I == 28) return go<28, 8, 5, 1>(P, W, io, st);
                 return go<32, 7, 5, 1>(P, W, io, st);
             }
+            if (I == 4) return go<4, 8, 8>(P, W, io, st);
             if (I == 8) return go<8, 4, 4>(P, W, io, st);
             if (I == 28) return go<28, 8, 6>(P, W, io, st);
             return go<32, 7, 5>(P, W, io, st);

@@ -60,14 +60,15 @@ struct mmpc_workspace {
     int variant;    // kernel variant the persistent state belongs to (1 = T1, 2 = T2, 3 = T3, 4 = T4)
 };
 
-// Tile width (instances per CTA) of kernel variant T4 for a handle of `batch` instances (mmpc_solve_t4.cuh): 8 while the batch
-// leaves at most one narrow tile per SM of a 148-SM B200, 32 beyond.  `forced` = kernel_variant >> 8 (1: 8, 2: 28, 3: 32).
-// The ABI layer cuts host-buffer sub-batches on multiples of it.
+// Tile width (instances per CTA) of kernel variant T4 for a handle of `batch` instances (mmpc_solve_t4.cuh): 4 (8 node slots per
+// instance, 64 threads, two CTAs per SM at most) while the batch is at most 8 * 148 instances, 32 beyond.  `forced` =
+// kernel_variant >> 8 (1: 8, 2: 28, 3: 32, 4: 4).  The ABI layer cuts host-buffer sub-batches on multiples of it.
 static inline int mmpc_t4_tile_width(int batch, int forced) {
     if (forced == 1) return 8;
     if (forced == 2) return 28;
+    if (forced == 4) return 4;
     if (forced >= 3) return 32;
-    return batch <= 148 * 8 ? 8 : 32;
+    return batch <= 148 * 8 ? 4 : 32;
 }
 
 struct mmpc_solve_io {

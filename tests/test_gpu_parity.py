@@ -180,8 +180,8 @@ def test_solve_vs_golden(api, golden):
 
 
 # 3 + 256*2 forces T3's 32-instance tile configuration (chosen automatically only for batches beyond 1184) on ragged small batches;
-# 4 + 256*k forces T4's tile width 4 / 14 / 28 (chosen from the batch size otherwise: 4 here)
-SOLVE_VARIANTS = [1, 2, 3, 3 + 256 * 2, 4 + 256 * 1, 4 + 256 * 2, 4 + 256 * 3]
+# 4 + 256*k forces T4's tile width 8 / 28 / 32 / 4 (chosen from the batch size otherwise: 4 here)
+SOLVE_VARIANTS = [1, 2, 3, 3 + 256 * 2, 4 + 256 * 1, 4 + 256 * 2, 4 + 256 * 3, 4 + 256 * 4]
 
 
 @pytest.mark.parametrize("variant", SOLVE_VARIANTS)

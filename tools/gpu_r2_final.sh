@@ -1,8 +1,8 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/final_pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/final_pytest.log
+python -m pytest tests -m gpu -q > gpurun_out/final_pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/final_pytest.log
 tail -3 gpurun_out/final_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-build/examples/ex_prototype_mpc 2>&1 | tail -4
+
 python bench.py > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/final_bench.err; echo "bench rc $?"
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2>/dev/null; echo "ref rc $?"
 python - <<'PY'
