@@ -245,9 +245,10 @@ __device__ __noinline__ void t4_forward(const T3Ctx<M, C::I, C::MODE>& cin, doub
             long long tw = t0;
 #endif
             issue_loads(ch + 1, ch);
-            if (act && ch > 0 && wj < min(C::CF, N - (ch - 1) * C::CF)) {  // the iterate rows post_node updates -> L1
-                const int k = (ch - 1) * C::CF + wj;
-                MMPC_UNROLL for (int a = 0; a < S; ++a) t3_prefetch(c.V + ((size_t)k * S + NX + a) * I);
+            if (wj < min(C::CF, N - ch * C::CF)) {  // what the NEXT step's post-processing reads from global memory -> L1, one step ahead
+                const int k = ch * C::CF + wj;
+                if (act) { MMPC_UNROLL for (int a = 0; a < S; ++a) t3_prefetch(c.V + ((size_t)k * S + NX + a) * I); }
+                else { MMPC_UNROLL for (int a = 0; a < NX; ++a) t3_prefetch(c.LAM + ((size_t)k * NX + a) * I); }
             }
             T4_STAMPW(6, tw);
             if (ch > 0) post_chunk(ch - 1);
