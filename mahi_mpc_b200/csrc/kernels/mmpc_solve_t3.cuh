@@ -323,12 +323,12 @@ __device__ __forceinline__ bool t3_riccati_stage(T3Riccati<M>& V, const double* 
     MMPC_UNROLL for (int a = 0; a < NX * NX; ++a) Fx[a] = T3_FXNZ(a / NX, a % NX) ? T3_R(C::RB_FX + T3_FXSLOT(a)) : 0.0;
     MMPC_UNROLL for (int a = 0; a < NX * NU; ++a) Fu[a] = T3_FUNZ(a / NU, a % NU) ? T3_R(C::RB_FU + T3_FUSLOT(a)) : 0.0;
     MMPC_UNROLL for (int a = 0; a < NX; ++a) cres[a] = T3_R(C::RB_C + a);
-    // NOTE: keep `#pragma unroll` loops of an `if constexpr` branch inside braces.  `if constexpr (C::BD) MMPC_UNROLL for (...) {...}`
-    // expands to an `if constexpr` whose next token is a `#pragma unroll` line; nvcc 12.9's front end then takes the pragma as the
-    // (empty) controlled statement, so the loop that follows runs UNCONDITIONALLY -- here it would add the record fields RB_SN /
-    // RB_GN, which only exist in the bounded record layout, to the value function of the unbounded instantiations (observed as
-    // changed multipliers and one more Newton iteration; tools/it_cmp.py shows it).  Not an uninitialised read in this code: a
-    // statement-association quirk, avoided by the braces (and checked by the iteration-count parity tests against the oracle).
+    // NOTE: keep `#pragma unroll` loops of an `if constexpr` branch inside braces.  With nvcc 12.9 the form
+    // `if constexpr (C::BD) _Pragma("unroll") for (...) {...}` changed the multipliers this function's callers computed in the
+    // instantiations where the branch is discarded (one more Newton iteration per solve; tools/it_cmp.py shows it).  The cause is
+    // not established: a minimal reproducer of the construct (an `if constexpr` followed by a pragma line and a loop) discards
+    // the loop correctly in PTX, and compute-sanitizer is not available on this GPU pool.  The braced form is what the
+    // iteration-count parity tests against the oracle (every variant, all 4096 instances of the bench batch) pin.
     if constexpr (C::BD != 0) {  // barrier of x_{k+1}: part of the value function of stage k+1
         MMPC_UNROLL for (int a = 0; a < NX; ++a) {
             V.Pxx[a * NX + a] += T3_R(C::RB_SN + a);
