@@ -95,6 +95,15 @@ int main() {
         const auto u0 = bmc.first_control(b);
         CHECK(std::fabs(u0[0] - u_free[0]) < 1e-6 && std::fabs(u0[1] - u_free[1]) < 1e-6);
     }
+    // the same batch sharded over "several" devices (two shards on device 0: the parity box has one GPU): same plans
+    BatchModelControl sharded(name, B, std::vector<int>{0, 0}, {10, 1, 5, 5}, {5, 5}, {1, 1}, opts);
+    const std::vector<double>& Vs = sharded.calc_u(states, controls, trajs);
+    const std::vector<double>& V1 = bmc.calc_u(states, controls, trajs);  // warm start from the first call: converges at once
+    CHECK(Vs.size() == V1.size());
+    for (size_t q = 0; q < Vs.size(); ++q) CHECK(std::fabs(Vs[q] - V1[q]) < 1e-6);
+    for (int b = 0; b < B; ++b) CHECK(sharded.status()[b] == 0);
+    sharded.update_weights({10, 1, 5, 5});
+    sharded.reset_warm_start();
     bool threw = false;
     try { bmc.calc_u(states, controls, ref1); } catch (const std::invalid_argument&) { threw = true; }
     CHECK(threw);
