@@ -185,7 +185,12 @@ int mmpc_reset_warm_start(mmpc_solver_t solver);
  *   lam_out[B*M]  constraint multipliers (may be NULL)
  *   stats[B]      (may be NULL)
  * For is_linear models A, B, xdot_init are computed on the device at (state, control)
- * (ModelControl.cpp:125-135). */
+ * (ModelControl.cpp:125-135).
+ * MMPC_MEM_HOST transfers: (1) small batches (staging <= 256 KB, e.g. one calc_u) are copied into the handle's page-locked
+ * staging buffers, which the tile kernels read and write IN PLACE over PCIe (zero-copy: one launch + one synchronisation, no
+ * copy-engine transfers; MMPC_ZERO_COPY=0 restores the packed H2D / D2H copies); (2) page-locked caller buffers that the device
+ * can address (cudaHostAlloc / cudaHostRegister, torch pin_memory()) are used in place the same way, in up to 8 sub-batches on
+ * their own streams (MMPC_ZC_BIG=0: copy engines); (3) pageable buffers go through cudaMemcpyAsync.  Same bits on every path. */
 int mmpc_solve(mmpc_solver_t solver, const double* state, const double* control, const double* traj, double* V_out,
                double* lam_out, mmpc_stats* stats, mmpc_mem mem, void* stream);
 
@@ -204,7 +209,8 @@ int mmpc_closed_loop(mmpc_solver_t solver, int cycles, int plant_integrator, dou
 
 /* Time of the device work of the last mmpc_solve on this handle in milliseconds (CUDA events on the
  * launching stream): [0] H2D staging, [1] kernels, [2] D2H staging.  Host-buffer calls that are pipelined over sub-batches
- * (batches >= 4096) report the whole H2D + solve + D2H span in [1] and zeros in [0], [2].
+ * (batches >= 4096) report the whole H2D + solve + D2H span in [1] and zeros in [0], [2]; zero-copy small-batch calls report
+ * launch .. synchronised on the HOST clock in [1] (no events are recorded on that path) and zeros in [0], [2].
  * Tracing: every entry point opens an NVTX range ("mmpc_solve", ...); with MMPC_STATS_JSONL=<path> in the environment every
  * host-buffer mmpc_solve that returns statistics appends one JSON line (batch, N, kernel variant, times, iteration and
  * status counts) to <path>. */

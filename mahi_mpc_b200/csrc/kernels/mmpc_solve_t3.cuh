@@ -171,6 +171,92 @@ struct T3Ctx : T3CtxBounds<M, ((MODE_ >> 1) & 1) != 0> {
 // L2 -> L1 prefetch of the iterate rows node k's evaluation reads (issued one chunk ahead: the evaluation otherwise
 // starts with a dependent chain of L2 round trips)
 __device__ __forceinline__ void t3_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// Zero-copy inputs (mmpc_solve_io::traj_stage != NULL): state / control / traj point into page-locked HOST memory.  The CTA brings
+// the rows of its tile's instances [bA, bB) on the device once, with coalesced loads (consecutive threads, consecutive words: whole
+// PCIe read requests) issued eight at a time per thread so that few round trips cover them, and reads the device copies from then
+// on (the reference trajectories are read in every sweep).  Ends with a CTA barrier that publishes the copies to the tile.
+struct T3Inputs {
+    const double *state, *control, *traj;
+};
+template <int THREADS>
+__device__ __forceinline__ void t3_stage_rows(const double* __restrict__ src, double* __restrict__ dst, int n, int tid) {
+    constexpr int UB = 8;
+    for (int e0 = tid; e0 < n; e0 += UB * THREADS) {
+        double t[UB];
+        MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * THREADS < n) t[q] = __ldcv(src + e0 + q * THREADS);
+        MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * THREADS < n) dst[e0 + q * THREADS] = t[q];
+    }
+}
+template <int THREADS, int NX, int NU>
+__device__ __forceinline__ T3Inputs t3_stage_inputs(const mmpc_solve_io& io, int tid, int bA, int bB, int N) {
+    T3Inputs in{io.state, io.control, io.traj};
+    if (!io.traj_stage) return in;  // uniform over the grid
+    const int nb = bB - bA;
+    // the two short rows first, their loads in flight together with the first batch of the trajectories' loads
+    const int ns = nb * NX, nc = nb * NU;
+    double ts = 0.0, tc = 0.0;
+    const bool small = ns <= THREADS && nc <= THREADS;
+    if (small) {
+        if (tid < ns) ts = __ldcv(io.state + (size_t)bA * NX + tid);
+        if (tid < nc) tc = __ldcv(io.control + (size_t)bA * NU + tid);
+    } else {
+        t3_stage_rows<THREADS>(io.state + (size_t)bA * NX, io.state_stage + (size_t)bA * NX, ns, tid);
+        t3_stage_rows<THREADS>(io.control + (size_t)bA * NU, io.control_stage + (size_t)bA * NU, nc, tid);
+    }
+    t3_stage_rows<THREADS>(io.traj + (size_t)bA * N * NX, io.traj_stage + (size_t)bA * N * NX, nb * N * NX, tid);
+    if (small) {
+        if (tid < ns) io.state_stage[(size_t)bA * NX + tid] = ts;
+        if (tid < nc) io.control_stage[(size_t)bA * NU + tid] = tc;
+    }
+    __syncthreads();
+    in.state = io.state_stage; in.control = io.control_stage; in.traj = io.traj_stage;
+    return in;
+}
+// Zero-copy outputs (mmpc_solve_io::host_out): V_out / lam_out / stats point into page-locked HOST memory and are written by the
+// kernel in place (posted PCIe writes).  The iterate lives tile-major ([element][instance]), the outputs are instance-major: the
+// plain epilogue's stores (lane = instance, 8 bytes every NV * 8 bytes) would leave the SM as 8-byte PCIe writes.  Here 64 elements of
+// every instance pass through shared memory at a time, so each warp stores 256 contiguous bytes of one instance's vector.
+template <int THREADS, int I>
+__device__ __forceinline__ void t3_rows_to_host(double* smem, const double* __restrict__ src_tile, double* __restrict__ dst, int rowlen,
+                                                int nvalid, int tid) {
+    constexpr int E = 64, LD = E + 1, UB = 8;
+    for (int e0 = 0; e0 < rowlen; e0 += E) {
+        const int ne = min(E, rowlen - e0), n = ne * I;
+        const double* src = src_tile + (size_t)e0 * I;
+        __syncthreads();  // the previous chunk (or whatever used this shared memory before) has been consumed
+        for (int t0 = tid; t0 < n; t0 += UB * THREADS) {
+            double v[UB];
+            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (t0 + q * THREADS < n) v[q] = src[t0 + q * THREADS];
+            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (t0 + q * THREADS < n) {
+                const int t = t0 + q * THREADS;
+                smem[(t % I) * LD + t / I] = v[q];
+            }
+        }
+        __syncthreads();
+        for (int t = tid; t < nvalid * E; t += THREADS) {
+            const int ii = t / E, r = t % E;
+            if (r < ne) __stcs(&dst[(size_t)ii * rowlen + e0 + r], smem[ii * LD + r]);
+        }
+    }
+}
+template <int THREADS, int I>
+__device__ __forceinline__ void t3_outputs_to_host(double* smem, const mmpc_solve_io& io, int tile, int tid, int NV, int Mc,
+                                                   const double* V_tile, const double* LAM_tile, double* Lcan_tile, const mmpc_stats& st) {
+    static_assert(sizeof(mmpc_stats) == 5 * sizeof(double), "stats rows are copied as five words");
+    const int nvalid = min(I, io.b1 - tile * I);
+    t3_rows_to_host<THREADS, I>(smem, V_tile, io.V_out + (size_t)tile * I * NV, NV, nvalid, tid);
+    if (io.lam_out) t3_rows_to_host<THREADS, I>(smem, LAM_tile, io.lam_out + (size_t)tile * I * Mc, Mc, nvalid, tid);
+    if (Lcan_tile) for (int t = tid; t < Mc * I; t += THREADS) Lcan_tile[t] = LAM_tile[t];  // warm start: same tile layout
+    if (io.stats) {
+        __syncthreads();
+        if (tid < I) reinterpret_cast<mmpc_stats*>(smem)[tid] = st;
+        __syncthreads();
+        double* dst = reinterpret_cast<double*>(io.stats + (size_t)tile * I);
+        for (int t = tid; t < nvalid * 5; t += THREADS) __stcs(&dst[t], smem[t]);
+    }
+}
+
 template <class M, class C>
 __device__ __forceinline__ void t3_prefetch_node(const T3Ctx<M, C::I, C::MODE>& c, int k) {
     constexpr int NX = M::NX, S = C::S, I = C::I;
@@ -989,7 +1075,8 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
         c.ZL = W.ZL2 + (size_t)tile * I * NV + i; c.ZU = W.ZU2 + (size_t)tile * I * NV + i;
         c.DZL = W.DZL2 + (size_t)tile * I * NV + i; c.DZU = W.DZU2 + (size_t)tile * I * NV + i;
     }
-    c.traj = io.traj + (size_t)bi * N * NX;
+    const T3Inputs in = t3_stage_inputs<C::THREADS, NX, NU>(io, tid, max(tile * I, io.b0), min(tile * I + I, io.b1), N);
+    c.traj = in.traj + (size_t)bi * N * NX;
     double* fg_tile = W.FG2 + (size_t)tile * I * N * C::FG;
     double* kg_tile = W.KG2 + (size_t)tile * I * N * C::KG;
     double* pg_tile = W.PG2 + (size_t)tile * I * N * C::PG;
@@ -997,7 +1084,7 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
     MMPC_UNROLL for (int a = 0; a < NU; ++a) {
         c.R[a] = W.Rw[(size_t)a * W.Bp + bi];
         c.Rm[a] = W.Rmw[(size_t)a * W.Bp + bi];
-        c.uinit[a] = io.control[(size_t)bi * NU + a];
+        c.uinit[a] = in.control[(size_t)bi * NU + a];
     }
     // ---- start point (ModelControl.cpp:28-50,68 cold; :161 warm), x_0 pinned (:144-145); the C workers of an instance help ----
     const bool warm = io.warm_start && W.have_warm;
@@ -1005,7 +1092,7 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
         if (!warm) for (int e = NX + j; e < NV; e += C::CB) c.V[(size_t)e * I] = 0.0;
         if (!(warm && io.warm_start_duals)) for (int e = j; e < Mc; e += C::CB) c.LAM[(size_t)e * I] = 0.0;
         for (int e = j; e < NX; e += C::CB) {
-            c.V[(size_t)e * I] = io.state[(size_t)bi * NX + e];
+            c.V[(size_t)e * I] = in.state[(size_t)bi * NX + e];
             c.DV[(size_t)e * I] = 0.0;
         }
     }
@@ -1268,6 +1355,13 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
     // steps the multipliers are copied back there ----
     double* const Lcan = W.LAM2 + (size_t)tile * I * Mc + i;
     const bool back = c.LAM != Lcan;  // tile-uniform
+    if (io.host_out) {
+        mmpc_stats s;
+        s.objective = fval; s.kkt_error = err; s.mu = mu; s.iterations = it_done; s.status = status;
+        s.ls_steps = ls_total; s.reg_steps = reg_total;
+        t3_outputs_to_host<C::THREADS, I>(smem, io, tile, tid, NV, Mc, Vp - i, c.LAM - i, back ? Lcan - i : nullptr, s);
+        return;
+    }
     if (worker) {
         const double* LAMp = c.LAM;
         constexpr int UB = 8;  // batched so that the loads of one batch are in flight together

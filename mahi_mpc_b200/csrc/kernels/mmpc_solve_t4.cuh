@@ -415,7 +415,8 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
     c.V = W.V2 + (size_t)tile * I * NV + i; c.LAM = W.LAM2 + (size_t)tile * I * Mc + i;
     c.DV = W.DV2 + (size_t)tile * I * NV + i; c.LAMN = W.LAMN2 + (size_t)tile * I * Mc + i;
     c.LINp = W.LIN2 + (size_t)b * C::LIN;
-    c.traj = io.traj + (size_t)bi * N * NX;
+    const T3Inputs in = t3_stage_inputs<C::THREADS, NX, NU>(io, tid, max(tile * I, io.b0), min(tile * I + I, io.b1), N);
+    c.traj = in.traj + (size_t)bi * N * NX;
     // node records of the tile: FG2, KG2, PG2 are one contiguous region of the arena (mmpc_api.cu), used here as [node][REC rows][I]
     double* fg_tile = W.FG2 + (size_t)tile * I * N * C::REC;
     double* kg_tile = fg_tile + (size_t)C::REC_K * I;
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
     MMPC_UNROLL for (int a = 0; a < NU; ++a) {
         c.R[a] = W.Rw[(size_t)a * W.Bp + bi];
         c.Rm[a] = W.Rmw[(size_t)a * W.Bp + bi];
-        c.uinit[a] = io.control[(size_t)bi * NU + a];
+        c.uinit[a] = in.control[(size_t)bi * NU + a];
     }
     // ---- start point (ModelControl.cpp:28-50,68 cold; :161 warm), x_0 pinned (:144-145); the C workers of an instance help ----
     const bool warm = io.warm_start && W.have_warm;
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
         if (!warm) for (int e = NX + j; e < NV; e += C::CB) c.V[(size_t)e * I] = 0.0;
         if (!(warm && io.warm_start_duals)) for (int e = j; e < Mc; e += C::CB) c.LAM[(size_t)e * I] = 0.0;
         for (int e = j; e < NX; e += C::CB) {
-            c.V[(size_t)e * I] = io.state[(size_t)bi * NX + e];
+            c.V[(size_t)e * I] = in.state[(size_t)bi * NX + e];
             c.DV[(size_t)e * I] = 0.0;
         }
     }
@@ -571,6 +572,13 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
     // steps the multipliers are copied back there ----
     double* const Lcan = W.LAM2 + (size_t)tile * I * Mc + i;
     const bool back = c.LAM != Lcan;  // tile-uniform
+    if (io.host_out) {
+        mmpc_stats s;
+        s.objective = fval; s.kkt_error = err; s.mu = 0.0; s.iterations = it_done; s.status = status;
+        s.ls_steps = ls_total; s.reg_steps = reg_total;
+        t3_outputs_to_host<C::THREADS, I>(smem, io, tile, tid, NV, Mc, Vp - i, c.LAM - i, back ? Lcan - i : nullptr, s);
+        return;
+    }
     if (worker) {
         const double* LAMp = c.LAM;
         constexpr int UB = 8;  // batched so that the loads of one batch are in flight together

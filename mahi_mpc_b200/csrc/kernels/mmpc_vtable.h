@@ -6,7 +6,7 @@
 
 #define MMPC_MAXNX 16
 #define MMPC_MAXNU 8
-#define MMPC_VTABLE_VERSION 8
+#define MMPC_VTABLE_VERSION 9
 
 struct mmpc_stats;  // public struct (include/mahi_mpc_b200.h)
 
@@ -78,6 +78,14 @@ struct mmpc_solve_io {
     double tol, mu_init;
     int max_iter, warm_start, warm_start_duals, variant;
     int b0, b1;  // instance range [b0, b1) of this launch (b0 a multiple of 32): lets the ABI layer pipeline sub-batches
+    // Zero-copy inputs (T3 / T4): when traj_stage != NULL, state / control / traj point into page-locked HOST memory that the
+    // device reads in place over PCIe (no copy-engine transfers before the kernel): each CTA first copies the rows of its tile's
+    // instances into these device buffers (same indexing as the inputs) and reads them from there -- the reference trajectories
+    // are read in every sweep.  NULL: the inputs are device memory and are read in place.
+    double *state_stage, *control_stage, *traj_stage;
+    // Zero-copy outputs (T3 / T4): V_out / lam_out / stats point into page-locked HOST memory; the kernel writes them in place
+    // with a transposing epilogue (whole 256-byte runs per warp instead of 8-byte PCIe writes).  0: device memory, plain epilogue.
+    int host_out;
 };
 
 struct mmpc_model_vtable {

@@ -663,8 +663,9 @@ def test_group_solve_shards_and_gathers(api):
 
 
 def test_small_batch_packed_staging_and_stats_jsonl(api, coracle, tmp_path):
-    """B = 1 (one ModelControl::calc_u): the packed pinned staging path gives the oracle's plan; mmpc_last_timing reports
-    the three phases; MMPC_STATS_JSONL appends one line per solve."""
+    """B = 1 (one ModelControl::calc_u): the zero-copy path (the kernel reads / writes the page-locked staging buffers in place) gives
+    the oracle's plan, and so does the packed-copy path (MMPC_ZERO_COPY=0) -- bit for bit the same one; mmpc_last_timing reports
+    the phases; MMPC_STATS_JSONL appends one line per solve."""
     import json, subprocess, sys
     N = 25
     P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, 1)
@@ -673,8 +674,29 @@ def test_small_batch_packed_staging_and_stats_jsonl(api, coracle, tmp_path):
     s = api.Solver(m, 1, tol=1e-10, warm_start=0); s.set_weights(Q, R, Rm)
     V, lam, st = s.solve(x0, up, traj)
     assert st["status"][0] == 0 and np.abs(V - Vo).max() < U_ATOL
+    assert abs(st["objective"][0] - sto["f"][0]) <= 1e-8 * abs(sto["f"][0]) and abs(int(st["iterations"][0]) - int(sto["iters"][0])) <= 1
     t = s.last_timing()
-    assert t["h2d_ms"] > 0 and t["kernel_ms"] > 0 and t["d2h_ms"] > 0
+    assert t["h2d_ms"] == 0 and t["kernel_ms"] > 0 and t["d2h_ms"] == 0  # zero-copy: the transfers are the kernel's own loads / stores
+    # ragged small batches through the zero-copy path (tile width 4: full tiles, a partial tile, several CTAs), multipliers included
+    for B in (3, 4, 9, 33):
+        P, (Q, R, Rm), x0b, upb, trajb, pb = _solve_inputs(N, B)
+        Vob, lamo, stob, bad = coracle.solve_batch("double_pendulum", N, P.h, False, x0b, pb, tol=1e-10)
+        sb = api.Solver(m, B, tol=1e-10, warm_start=0); sb.set_weights(Q, R, Rm)
+        Vb, lamb, stb = sb.solve(x0b, upb, trajb)
+        assert bad == 0 and (stb["status"] == 0).all() and np.abs(stb["iterations"] - stob["iters"]).max() <= 1
+        assert np.abs(Vb - Vob).max() < U_ATOL and np.abs(stb["objective"] - stob["f"]).max() <= 1e-8 * np.abs(stob["f"]).max()
+        V2, lam2, st2 = sb.solve(x0b, upb, trajb)  # the staging buffers are reused: the same bits again
+        assert np.array_equal(V2, Vb) and np.array_equal(lam2, lamb)
+    # the packed-copy path in a child process (the switch is read once): the same bits, three phases
+    np.save(tmp_path / "V_zc.npy", V)
+    code = ("import numpy as np, mahi_mpc_b200.api as api; from oracle import nlp;"
+            "P = nlp.Problem(N=25); Q, R, Rm = nlp.default_weights(4, 2); x0, up, traj = nlp.synthetic_batch(4, 2, 25, P.h, 1);"
+            "m = api.Model('double_pendulum', N=25); s = api.Solver(m, 1, tol=1e-10, warm_start=0); s.set_weights(Q, R, Rm);"
+            "V, lam, st = s.solve(x0, up, traj); t = s.last_timing();"
+            "assert t['h2d_ms'] > 0 and t['kernel_ms'] > 0 and t['d2h_ms'] > 0, t;"
+            f"assert np.array_equal(V, np.load(r'{tmp_path / 'V_zc.npy'}'))")
+    subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, MMPC_ZERO_COPY="0"),
+                   cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     # the environment variable is read once per process: a child process writes the file
     out = tmp_path / "stats.jsonl"
     code = ("import numpy as np, mahi_mpc_b200.api as api; from mahi_mpc_b200 import workload as w;"
@@ -685,6 +707,35 @@ def test_small_batch_packed_staging_and_stats_jsonl(api, coracle, tmp_path):
     subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     lines = [json.loads(l) for l in out.read_text().splitlines()]
     assert len(lines) == 2 and lines[0]["batch"] == 5 and lines[0]["converged"] == 5 and lines[0]["kernel_ms"] > 0 and lines[0]["N"] == 25
+
+
+def test_pinned_host_buffers_zero_copy_matches_device_resident(api):
+    """Page-locked caller buffers (torch pin_memory) are read and written by the tile kernels in place (zero-copy inputs staged per
+    tile, transposing epilogue for the outputs, sub-batches on their own streams): the plans, multipliers and statistics must be
+    the bits of the device-resident solve -- full batches, a ragged one (partial last tile and sub-batch) and a bounded one (T3)."""
+    import torch
+    N = 50
+    m = api.Model("double_pendulum", N=N)
+    for B, bounded in ((4096, False), (4096 + 37, False), (1500, False), (4096, True)):
+        P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B)
+        s = api.Solver(m, B, tol=1e-8, warm_start=0); s.set_weights(Q, R, Rm)
+        if bounded:
+            s.set_bounds(u_min=[-2.0, -2.0], u_max=[2.0, 2.0])
+        d = [torch.from_numpy(a).cuda() for a in (x0, up, traj)]
+        Vd, lamd, std = s.solve(*d)
+        h = [torch.from_numpy(a).pin_memory() for a in (x0, up, traj)]
+        Vh = torch.empty(B, m.NV, dtype=torch.float64).pin_memory(); lamh = torch.empty(B, m.M, dtype=torch.float64).pin_memory()
+        sth = torch.empty(B, 5, dtype=torch.float64).pin_memory()
+        Vh.fill_(float("nan")); lamh.fill_(float("nan"))
+        s.solve(*h, V_out=Vh, lam_out=lamh, stats_out=sth)
+        assert torch.equal(Vh, Vd.cpu()) and torch.equal(lamh, lamd.cpu()), (B, bounded)
+        a, b = api.stats_from_tensor(sth), api.stats_from_tensor(std)
+        assert np.array_equal(a["iterations"], b["iterations"]) and np.array_equal(a["status"], b["status"]) and np.array_equal(a["objective"], b["objective"])
+        assert (a["status"] == 0).mean() > (0.95 if bounded else 0.999)
+        # pageable buffers (copy engines) give the same bits too
+        Vp, lamp, stp = s.solve(x0, up, traj)
+        assert np.array_equal(Vp, Vd.cpu().numpy()) and np.array_equal(lamp, lamd.cpu().numpy())
+        s.close()
 
 
 # ---------------------------------------------------------------------------------------------------------------
