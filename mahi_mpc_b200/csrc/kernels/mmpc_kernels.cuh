@@ -549,42 +549,81 @@ struct Launch {
         return cudaGetLastError();
     }
     // per-variant launchers; each may live in its own translation unit (MMPC_DEFINE_SOLVE_T*)
+    // T1's two instantiations (free / interior point) are the longest single kernels to compile: one translation unit each
+    template <bool BOUNDED>
     static cudaError_t solve_t1(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         const int grid = (io.b1 - io.b0 + 31) / 32;
-        if (P.bounded) solve_kernel_t1<M, true><<<grid, 32, 0, st>>>(P, W, io);
-        else solve_kernel_t1<M, false><<<grid, 32, 0, st>>>(P, W, io);
+        solve_kernel_t1<M, BOUNDED><<<grid, 32, 0, st>>>(P, W, io);
         return cudaGetLastError();
     }
     static cudaError_t solve_t2(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         return LaunchT2<M>::run(P, W, io, st);
     }
+    template <int PART>
     static cudaError_t solve_t3(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
-        return LaunchT3<M>::run(P, W, io, st);
+        return LaunchT3<M>::template run_part<PART>(P, W, io, st);
     }
+    template <int PART>
     static cudaError_t solve_t4(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
-        return LaunchT4<M>::run(P, W, io, st);
+        return LaunchT4<M>::template run_part<PART>(P, W, io, st);
     }
 };
 
 }  // namespace mmpc
 
 // ---- translation-unit macros --------------------------------------------------------------------------------
-// The three solve variants of a model can be compiled in separate units (parallel builds of large generated models):
+// The solve variants of a model can be compiled in separate units (parallel builds of large generated models):
 #define MMPC_DEFINE_SOLVE_T1(MODEL)                                                                                    \
+    extern "C" cudaError_t mmpc_solve_t1b_##MODEL(const mmpc_problem*, const mmpc_workspace*, const mmpc_solve_io*, cudaStream_t); \
     extern "C" cudaError_t mmpc_solve_t1_##MODEL(const mmpc_problem* P, const mmpc_workspace* W, const mmpc_solve_io* io, cudaStream_t st) { \
-        return mmpc::Launch<mmpc_model_##MODEL>::solve_t1(*P, *W, *io, st);                                             \
+        if (P->bounded) return mmpc_solve_t1b_##MODEL(P, W, io, st);                                                    \
+        return mmpc::Launch<mmpc_model_##MODEL>::solve_t1<false>(*P, *W, *io, st);                                      \
+    }
+#define MMPC_DEFINE_SOLVE_T1B(MODEL)                                                                                   \
+    extern "C" cudaError_t mmpc_solve_t1b_##MODEL(const mmpc_problem* P, const mmpc_workspace* W, const mmpc_solve_io* io, cudaStream_t st) { \
+        return mmpc::Launch<mmpc_model_##MODEL>::solve_t1<true>(*P, *W, *io, st);                                       \
     }
 #define MMPC_DEFINE_SOLVE_T2(MODEL)                                                                                    \
     extern "C" cudaError_t mmpc_solve_t2_##MODEL(const mmpc_problem* P, const mmpc_workspace* W, const mmpc_solve_io* io, cudaStream_t st) { \
         return mmpc::Launch<mmpc_model_##MODEL>::solve_t2(*P, *W, *io, st);                                             \
     }
+// T3 / T4: part 0 (with the dispatcher over the parts) and one unit per further part (LaunchT3 / LaunchT4::run_part)
+#define MMPC_SOLVE_FN_ARGS const mmpc_problem* P, const mmpc_workspace* W, const mmpc_solve_io* io, cudaStream_t st
 #define MMPC_DEFINE_SOLVE_T3(MODEL)                                                                                    \
-    extern "C" cudaError_t mmpc_solve_t3_##MODEL(const mmpc_problem* P, const mmpc_workspace* W, const mmpc_solve_io* io, cudaStream_t st) { \
-        return mmpc::Launch<mmpc_model_##MODEL>::solve_t3(*P, *W, *io, st);                                             \
+    extern "C" cudaError_t mmpc_solve_t3p1_##MODEL(MMPC_SOLVE_FN_ARGS);                                                 \
+    extern "C" cudaError_t mmpc_solve_t3p2_##MODEL(MMPC_SOLVE_FN_ARGS);                                                 \
+    extern "C" cudaError_t mmpc_solve_t3_##MODEL(MMPC_SOLVE_FN_ARGS) {                                                  \
+        const int part = mmpc::LaunchT3<mmpc_model_##MODEL>::part_of(*P);                                               \
+        if (part == 1) return mmpc_solve_t3p1_##MODEL(P, W, io, st);                                                    \
+        if (part == 2) return mmpc_solve_t3p2_##MODEL(P, W, io, st);                                                    \
+        return mmpc::Launch<mmpc_model_##MODEL>::solve_t3<0>(*P, *W, *io, st);                                          \
     }
+#define MMPC_DEFINE_SOLVE_T3_PART(MODEL, K)                                                                            \
+    extern "C" cudaError_t mmpc_solve_t3p##K##_##MODEL(MMPC_SOLVE_FN_ARGS) {                                            \
+        return mmpc::Launch<mmpc_model_##MODEL>::solve_t3<K>(*P, *W, *io, st);                                          \
+    }
+// MMPC_DEFAULT_TILES_ONLY (set by ModelGenerator::compile_model): parts 1 and 3 -- tile widths that are only ever selected on
+// request (tests of other tile shapes, kernel_variant = 4 + 256 k) -- are not built for a user model; asking for them is
+// MMPC_ERR_UNSUPPORTED.
+#ifdef MMPC_DEFAULT_TILES_ONLY
+#define MMPC_T4_EXTRA_PART(MODEL, K) cudaErrorNotSupported
+#else
+#define MMPC_T4_EXTRA_PART(MODEL, K) mmpc_solve_t4p##K##_##MODEL(P, W, io, st)
+#endif
 #define MMPC_DEFINE_SOLVE_T4(MODEL)                                                                                    \
-    extern "C" cudaError_t mmpc_solve_t4_##MODEL(const mmpc_problem* P, const mmpc_workspace* W, const mmpc_solve_io* io, cudaStream_t st) { \
-        return mmpc::Launch<mmpc_model_##MODEL>::solve_t4(*P, *W, *io, st);                                             \
+    extern "C" cudaError_t mmpc_solve_t4p1_##MODEL(MMPC_SOLVE_FN_ARGS);                                                 \
+    extern "C" cudaError_t mmpc_solve_t4p2_##MODEL(MMPC_SOLVE_FN_ARGS);                                                 \
+    extern "C" cudaError_t mmpc_solve_t4p3_##MODEL(MMPC_SOLVE_FN_ARGS);                                                 \
+    extern "C" cudaError_t mmpc_solve_t4_##MODEL(MMPC_SOLVE_FN_ARGS) {                                                  \
+        const int part = mmpc::LaunchT4<mmpc_model_##MODEL>::part_of(*P, *W, *io);                                      \
+        if (part == 1) return MMPC_T4_EXTRA_PART(MODEL, 1);                                                             \
+        if (part == 2) return mmpc_solve_t4p2_##MODEL(P, W, io, st);                                                    \
+        if (part == 3) return MMPC_T4_EXTRA_PART(MODEL, 3);                                                             \
+        return mmpc::Launch<mmpc_model_##MODEL>::solve_t4<0>(*P, *W, *io, st);                                          \
+    }
+#define MMPC_DEFINE_SOLVE_T4_PART(MODEL, K)                                                                            \
+    extern "C" cudaError_t mmpc_solve_t4p##K##_##MODEL(MMPC_SOLVE_FN_ARGS) {                                            \
+        return mmpc::Launch<mmpc_model_##MODEL>::solve_t4<K>(*P, *W, *io, st);                                          \
     }
 // ... and this one defines the evaluators, the solve dispatcher and `mmpc_vtable_<MODEL>()`:
 #define MMPC_DEFINE_MODEL_CORE(MODEL)                                                                                   \
@@ -615,7 +654,10 @@ struct Launch {
     }
 // everything in one unit (what ModelGenerator::generate_c_code emits for a user model)
 #define MMPC_DEFINE_MODEL(MODEL) \
-    MMPC_DEFINE_SOLVE_T1(MODEL) MMPC_DEFINE_SOLVE_T2(MODEL) MMPC_DEFINE_SOLVE_T3(MODEL) MMPC_DEFINE_SOLVE_T4(MODEL) MMPC_DEFINE_MODEL_CORE(MODEL)
+    MMPC_DEFINE_SOLVE_T1(MODEL) MMPC_DEFINE_SOLVE_T1B(MODEL) MMPC_DEFINE_SOLVE_T2(MODEL)                                  \
+    MMPC_DEFINE_SOLVE_T3(MODEL) MMPC_DEFINE_SOLVE_T3_PART(MODEL, 1) MMPC_DEFINE_SOLVE_T3_PART(MODEL, 2)                    \
+    MMPC_DEFINE_SOLVE_T4(MODEL) MMPC_DEFINE_SOLVE_T4_PART(MODEL, 1) MMPC_DEFINE_SOLVE_T4_PART(MODEL, 2) MMPC_DEFINE_SOLVE_T4_PART(MODEL, 3) \
+    MMPC_DEFINE_MODEL_CORE(MODEL)
 // Additionally exports the generic entry point a stand-alone generated model library is dlopen'ed by
 // (the role `nlpsol("nlpsol","ipopt",dll,...)` plays at ModelControl.cpp:61-62).
 // Generated libraries are compiled with -fvisibility=hidden: only this entry is exported, so a user model whose

@@ -1435,31 +1435,25 @@ struct LaunchT3 {
     // Tried and slower: 14 x 8 x 4, 16 x 4 x 4, 32 x 4 x 4, 32 x 7 x {4, 6}, 32 x 6 x {4, 5} with warp 4 idle (SK).
     // The tile width fixes the layout of the persistent iterate, so the choice depends only on the batch size of the
     // handle.  kernel_variant = 3 + 256*k forces configuration k.
-    static cudaError_t run(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
+    // The instantiations are compiled as three parts, one translation unit each (MMPC_DEFINE_SOLVE_T3 / _T3_PART in mmpc_kernels.cuh):
+    //   part 0  Euler / linearised      part 1  finite bounds (interior point)      part 2  RK4 shooting
+    static int part_of(const mmpc_problem& P) { return P.bounded ? 1 : ((P.integrator == MMPC_RK4 && !P.is_linear) ? 2 : 0); }
+    template <int PART>
+    static cudaError_t run_part(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         if (P.node_cost) return cudaErrorNotSupported;  // MMPC_COST_NODE: T4 / T1 (T3's forward sweep has no terminal objective term)
         const int forced = io.variant >> 8;
         const int cfg = forced ? forced : (W.B > 8 * 148 ? 2 : 1);
-        if (P.bounded) {
-            // finite bounds: interior point (Euler / linearised steps; bounded RK4 solves stay on T1); small models only
-            if constexpr (M::NX + 2 * M::NU <= 8) {
+        if constexpr (PART == 0) return cfg == 2 ? go<32, 7, 5>(P, W, io, st) : go<8, 4, 4>(P, W, io, st);
+        // finite bounds: interior point (Euler / linearised steps; bounded RK4 solves stay on T1); RK4 shooting: dense sensitivities.
+        // Both are instantiated for the small models the tile kernels are the default for.
+        if constexpr (M::NX + 2 * M::NU <= 8) {
+            if constexpr (PART == 1) {
                 if (P.integrator == MMPC_RK4 && !P.is_linear) return cudaErrorNotSupported;
-                if (cfg == 2) return go<32, 6, 5, 0, 2>(P, W, io, st);
-                return go<8, 4, 4, 0, 2>(P, W, io, st);
-            } else {
-                return cudaErrorNotSupported;
+                return cfg == 2 ? go<32, 6, 5, 0, 2>(P, W, io, st) : go<8, 4, 4, 0, 2>(P, W, io, st);
             }
+            if constexpr (PART == 2) return cfg == 2 ? go<32, 7, 5, 0, 1>(P, W, io, st) : go<8, 4, 4, 0, 1>(P, W, io, st);
         }
-        if (P.integrator == MMPC_RK4 && !P.is_linear) {
-            // RK4 shooting (dense sensitivities, Gauss-Newton Hessian); instantiated for the small models T3 is the default for
-            if constexpr (M::NX + 2 * M::NU <= 8) {
-                if (cfg == 2) return go<32, 7, 5, 0, 1>(P, W, io, st);
-                return go<8, 4, 4, 0, 1>(P, W, io, st);
-            } else {
-                return cudaErrorNotSupported;
-            }
-        }
-        if (cfg == 2) return go<32, 7, 5>(P, W, io, st);
-        return go<8, 4, 4>(P, W, io, st);
+        return cudaErrorNotSupported;
     }
 };
 

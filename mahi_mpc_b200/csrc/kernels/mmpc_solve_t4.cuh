@@ -649,23 +649,25 @@ struct LaunchT4 {
     // kernel_variant = 4 + 256*k forces configuration k (1: 8, 2: 28, 3: 32, 4: 4).  Measured at N = 50 (profiles/r2_t4_configs.txt):
     //   B = 4 / 32 / 296 / 592 / 1184 / 2368:  4 x 8 x 8: 0.190 / 0.212 / 0.225 / 0.224 / 0.232 / 0.342 ms,  8 x 4 x 4: 0.218 / 0.250 /
     //   0.251 / 0.266 / 0.268 / 0.302 ms.
-    static cudaError_t run(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
+    // The instantiations are compiled as four parts, one translation unit each (MMPC_DEFINE_SOLVE_T4 / _T4_PART in mmpc_kernels.cuh:
+    // ModelGenerator::compile_model and the library build compile the units side by side):
+    //   part 0  Euler / linearised, tile widths 4 and 32 (the defaults)     part 1  Euler / linearised, widths 8 and 28
+    //   part 2  RK4 shooting, widths 4 and 32                               part 3  RK4 shooting, widths 8 and 28
+    static int part_of(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io) {
+        const int I = mmpc_t4_tile_width(W.B, io.variant >> 8);
+        return ((P.integrator == MMPC_RK4 && !P.is_linear) ? 2 : 0) + ((I == 4 || I == 32) ? 0 : 1);
+    }
+    template <int PART>
+    static cudaError_t run_part(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         if (P.bounded) return cudaErrorNotSupported;
         if constexpr (M::NX + 2 * M::NU <= 8) {
             const int I = mmpc_t4_tile_width(W.B, io.variant >> 8);
-            if (P.integrator == MMPC_RK4 && !P.is_linear) {
-                if (I == 4) return go<4, 8, 5, 1>(P, W, io, st);
-                if (I == 8) return go<8, 4, 4, 1>(P, W, io, st);
-                if (I == 28) return go<28, 8, 5, 1>(P, W, io, st);
-                return go<32, 7, 5, 1>(P, W, io, st);
-            }
-            if (I == 4) return go<4, 8, 8>(P, W, io, st);
-            if (I == 8) return go<8, 4, 4>(P, W, io, st);
-            if (I == 28) return go<28, 8, 6>(P, W, io, st);
-            return go<32, 7, 5>(P, W, io, st);
-        } else {
-            return cudaErrorNotSupported;
+            if constexpr (PART == 0) return I == 4 ? go<4, 8, 8>(P, W, io, st) : go<32, 7, 5>(P, W, io, st);
+            if constexpr (PART == 1) return I == 8 ? go<8, 4, 4>(P, W, io, st) : go<28, 8, 6>(P, W, io, st);
+            if constexpr (PART == 2) return I == 4 ? go<4, 8, 5, 1>(P, W, io, st) : go<32, 7, 5, 1>(P, W, io, st);
+            if constexpr (PART == 3) return I == 8 ? go<8, 4, 4, 1>(P, W, io, st) : go<28, 8, 5, 1>(P, W, io, st);
         }
+        return cudaErrorNotSupported;
     }
 };
 
