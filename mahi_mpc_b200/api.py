@@ -15,7 +15,8 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "libmahi_mpc_b200.so")
+# MMPC_LIB_PATH: developer aid for A/B timing of two builds of the library on one GPU box (tools/gpu_ab_lib.sh)
+LIB_PATH = os.environ.get("MMPC_LIB_PATH") or os.path.join(PKG, "lib", "libmahi_mpc_b200.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
 EULER, RK4 = 0, 1

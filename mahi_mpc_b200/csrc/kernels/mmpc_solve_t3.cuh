@@ -176,84 +176,79 @@ __device__ __forceinline__ void t3_prefetch(const void* p) { asm volatile("prefe
 // the rows of its tile's instances [bA, bB) on the device once, with coalesced loads (consecutive threads, consecutive words: whole
 // PCIe read requests) issued eight at a time per thread so that few round trips cover them, and reads the device copies from then
 // on (the reference trajectories are read in every sweep).  Ends with a CTA barrier that publishes the copies to the tile.
-struct T3Inputs {
-    const double *state, *control, *traj;
-};
-template <int THREADS>
-__device__ __forceinline__ void t3_stage_rows(const double* __restrict__ src, double* __restrict__ dst, int n, int tid) {
+// One non-inlined copy for all kernels, every argument by value: the solve kernels' own code (register allocation of the sweeps)
+// is the same with and without this path (inlined, it cost the device-resident solve 2-3 %: profiles/r2_latency.txt).
+__device__ __forceinline__ void t3_stage_rows(const double* __restrict__ src, double* __restrict__ dst, int n, int tid, int nthreads) {
     constexpr int UB = 8;
-    for (int e0 = tid; e0 < n; e0 += UB * THREADS) {
+    for (int e0 = tid; e0 < n; e0 += UB * nthreads) {
         double t[UB];
-        MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * THREADS < n) t[q] = __ldcv(src + e0 + q * THREADS);
-        MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * THREADS < n) dst[e0 + q * THREADS] = t[q];
+        MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * nthreads < n) t[q] = __ldcv(src + e0 + q * nthreads);
+        MMPC_UNROLL for (int q = 0; q < UB; ++q) if (e0 + q * nthreads < n) dst[e0 + q * nthreads] = t[q];
     }
 }
-template <int THREADS, int NX, int NU>
-__device__ __forceinline__ T3Inputs t3_stage_inputs(const mmpc_solve_io& io, int tid, int bA, int bB, int N) {
-    T3Inputs in{io.state, io.control, io.traj};
-    if (!io.traj_stage) return in;  // uniform over the grid
-    const int nb = bB - bA;
+static __device__ __noinline__ void t3_stage_inputs(const double* state, const double* control, const double* traj, double* state_stage,
+                                             double* control_stage, double* traj_stage, int bA, int bB, int nx, int nu, int N) {
+    const int tid = threadIdx.x, nthreads = blockDim.x, nb = bB - bA;
     // the two short rows first, their loads in flight together with the first batch of the trajectories' loads
-    const int ns = nb * NX, nc = nb * NU;
+    const int ns = nb * nx, nc = nb * nu;
     double ts = 0.0, tc = 0.0;
-    const bool small = ns <= THREADS && nc <= THREADS;
+    const bool small = ns <= nthreads && nc <= nthreads;
     if (small) {
-        if (tid < ns) ts = __ldcv(io.state + (size_t)bA * NX + tid);
-        if (tid < nc) tc = __ldcv(io.control + (size_t)bA * NU + tid);
+        if (tid < ns) ts = __ldcv(state + (size_t)bA * nx + tid);
+        if (tid < nc) tc = __ldcv(control + (size_t)bA * nu + tid);
     } else {
-        t3_stage_rows<THREADS>(io.state + (size_t)bA * NX, io.state_stage + (size_t)bA * NX, ns, tid);
-        t3_stage_rows<THREADS>(io.control + (size_t)bA * NU, io.control_stage + (size_t)bA * NU, nc, tid);
+        t3_stage_rows(state + (size_t)bA * nx, state_stage + (size_t)bA * nx, ns, tid, nthreads);
+        t3_stage_rows(control + (size_t)bA * nu, control_stage + (size_t)bA * nu, nc, tid, nthreads);
     }
-    t3_stage_rows<THREADS>(io.traj + (size_t)bA * N * NX, io.traj_stage + (size_t)bA * N * NX, nb * N * NX, tid);
+    t3_stage_rows(traj + (size_t)bA * N * nx, traj_stage + (size_t)bA * N * nx, nb * N * nx, tid, nthreads);
     if (small) {
-        if (tid < ns) io.state_stage[(size_t)bA * NX + tid] = ts;
-        if (tid < nc) io.control_stage[(size_t)bA * NU + tid] = tc;
+        if (tid < ns) state_stage[(size_t)bA * nx + tid] = ts;
+        if (tid < nc) control_stage[(size_t)bA * nu + tid] = tc;
     }
     __syncthreads();
-    in.state = io.state_stage; in.control = io.control_stage; in.traj = io.traj_stage;
-    return in;
 }
+
 // Zero-copy outputs (mmpc_solve_io::host_out): V_out / lam_out / stats point into page-locked HOST memory and are written by the
 // kernel in place (posted PCIe writes).  The iterate lives tile-major ([element][instance]), the outputs are instance-major: the
 // plain epilogue's stores (lane = instance, 8 bytes every NV * 8 bytes) would leave the SM as 8-byte PCIe writes.  Here 64 elements of
 // every instance pass through shared memory at a time, so each warp stores 256 contiguous bytes of one instance's vector.
-template <int THREADS, int I>
+// Non-inlined, arguments by value, tile width at run time (see t3_stage_inputs).
 __device__ __forceinline__ void t3_rows_to_host(double* smem, const double* __restrict__ src_tile, double* __restrict__ dst, int rowlen,
-                                                int nvalid, int tid) {
+                                                int nvalid, int tid, int nthreads, int I) {
     constexpr int E = 64, LD = E + 1, UB = 8;
     for (int e0 = 0; e0 < rowlen; e0 += E) {
         const int ne = min(E, rowlen - e0), n = ne * I;
         const double* src = src_tile + (size_t)e0 * I;
         __syncthreads();  // the previous chunk (or whatever used this shared memory before) has been consumed
-        for (int t0 = tid; t0 < n; t0 += UB * THREADS) {
+        for (int t0 = tid; t0 < n; t0 += UB * nthreads) {
             double v[UB];
-            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (t0 + q * THREADS < n) v[q] = src[t0 + q * THREADS];
-            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (t0 + q * THREADS < n) {
-                const int t = t0 + q * THREADS;
+            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (t0 + q * nthreads < n) v[q] = src[t0 + q * nthreads];
+            MMPC_UNROLL for (int q = 0; q < UB; ++q) if (t0 + q * nthreads < n) {
+                const int t = t0 + q * nthreads;
                 smem[(t % I) * LD + t / I] = v[q];
             }
         }
         __syncthreads();
-        for (int t = tid; t < nvalid * E; t += THREADS) {
+        for (int t = tid; t < nvalid * E; t += nthreads) {
             const int ii = t / E, r = t % E;
             if (r < ne) __stcs(&dst[(size_t)ii * rowlen + e0 + r], smem[ii * LD + r]);
         }
     }
 }
-template <int THREADS, int I>
-__device__ __forceinline__ void t3_outputs_to_host(double* smem, const mmpc_solve_io& io, int tile, int tid, int NV, int Mc,
-                                                   const double* V_tile, const double* LAM_tile, double* Lcan_tile, const mmpc_stats& st) {
+// The statistics are handed over through shared memory (the kernel's serial lanes store their mmpc_stats at smem + I * 65 doubles,
+// behind the transpose buffer): no solver state among the arguments.
+static __device__ __noinline__ void t3_outputs_to_host_s(double* smem, double* V_out, double* lam_out, mmpc_stats* stats, int b1, int tile, int I,
+                                                         int NV, int Mc, const double* V_tile, const double* LAM_tile, double* Lcan_tile) {
     static_assert(sizeof(mmpc_stats) == 5 * sizeof(double), "stats rows are copied as five words");
-    const int nvalid = min(I, io.b1 - tile * I);
-    t3_rows_to_host<THREADS, I>(smem, V_tile, io.V_out + (size_t)tile * I * NV, NV, nvalid, tid);
-    if (io.lam_out) t3_rows_to_host<THREADS, I>(smem, LAM_tile, io.lam_out + (size_t)tile * I * Mc, Mc, nvalid, tid);
-    if (Lcan_tile) for (int t = tid; t < Mc * I; t += THREADS) Lcan_tile[t] = LAM_tile[t];  // warm start: same tile layout
-    if (io.stats) {
-        __syncthreads();
-        if (tid < I) reinterpret_cast<mmpc_stats*>(smem)[tid] = st;
-        __syncthreads();
-        double* dst = reinterpret_cast<double*>(io.stats + (size_t)tile * I);
-        for (int t = tid; t < nvalid * 5; t += THREADS) __stcs(&dst[t], smem[t]);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int nvalid = min(I, b1 - tile * I);
+    t3_rows_to_host(smem, V_tile, V_out + (size_t)tile * I * NV, NV, nvalid, tid, nthreads, I);
+    if (lam_out) t3_rows_to_host(smem, LAM_tile, lam_out + (size_t)tile * I * Mc, Mc, nvalid, tid, nthreads, I);
+    if (Lcan_tile) for (int t = tid; t < Mc * I; t += nthreads) Lcan_tile[t] = LAM_tile[t];  // warm start: same tile layout
+    if (stats) {
+        const double* src = smem + I * 65;
+        double* dst = reinterpret_cast<double*>(stats + (size_t)tile * I);
+        for (int t = tid; t < nvalid * 5; t += nthreads) __stcs(&dst[t], src[t]);
     }
 }
 
@@ -1075,8 +1070,14 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
         c.ZL = W.ZL2 + (size_t)tile * I * NV + i; c.ZU = W.ZU2 + (size_t)tile * I * NV + i;
         c.DZL = W.DZL2 + (size_t)tile * I * NV + i; c.DZU = W.DZU2 + (size_t)tile * I * NV + i;
     }
-    const T3Inputs in = t3_stage_inputs<C::THREADS, NX, NU>(io, tid, max(tile * I, io.b0), min(tile * I + I, io.b1), N);
-    c.traj = in.traj + (size_t)bi * N * NX;
+    const double *in_state = io.state, *in_control = io.control;
+    c.traj = io.traj + (size_t)bi * N * NX;
+    if (io.traj_stage) {  // zero-copy inputs (uniform over the grid): the tile's rows are brought on the device first
+        t3_stage_inputs(io.state, io.control, io.traj, io.state_stage, io.control_stage, io.traj_stage, max(tile * I, io.b0),
+                        min(tile * I + I, io.b1), NX, NU, N);
+        in_state = io.state_stage; in_control = io.control_stage;
+        c.traj = io.traj_stage + (size_t)bi * N * NX;
+    }
     double* fg_tile = W.FG2 + (size_t)tile * I * N * C::FG;
     double* kg_tile = W.KG2 + (size_t)tile * I * N * C::KG;
     double* pg_tile = W.PG2 + (size_t)tile * I * N * C::PG;
@@ -1084,7 +1085,7 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
     MMPC_UNROLL for (int a = 0; a < NU; ++a) {
         c.R[a] = W.Rw[(size_t)a * W.Bp + bi];
         c.Rm[a] = W.Rmw[(size_t)a * W.Bp + bi];
-        c.uinit[a] = in.control[(size_t)bi * NU + a];
+        c.uinit[a] = in_control[(size_t)bi * NU + a];
     }
     // ---- start point (ModelControl.cpp:28-50,68 cold; :161 warm), x_0 pinned (:144-145); the C workers of an instance help ----
     const bool warm = io.warm_start && W.have_warm;
@@ -1092,7 +1093,7 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
         if (!warm) for (int e = NX + j; e < NV; e += C::CB) c.V[(size_t)e * I] = 0.0;
         if (!(warm && io.warm_start_duals)) for (int e = j; e < Mc; e += C::CB) c.LAM[(size_t)e * I] = 0.0;
         for (int e = j; e < NX; e += C::CB) {
-            c.V[(size_t)e * I] = in.state[(size_t)bi * NX + e];
+            c.V[(size_t)e * I] = in_state[(size_t)bi * NX + e];
             c.DV[(size_t)e * I] = 0.0;
         }
     }
@@ -1355,14 +1356,8 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
     // steps the multipliers are copied back there ----
     double* const Lcan = W.LAM2 + (size_t)tile * I * Mc + i;
     const bool back = c.LAM != Lcan;  // tile-uniform
-    if (io.host_out) {
-        mmpc_stats s;
-        s.objective = fval; s.kkt_error = err; s.mu = mu; s.iterations = it_done; s.status = status;
-        s.ls_steps = ls_total; s.reg_steps = reg_total;
-        t3_outputs_to_host<C::THREADS, I>(smem, io, tile, tid, NV, Mc, Vp - i, c.LAM - i, back ? Lcan - i : nullptr, s);
-        return;
-    }
-    if (worker) {
+    const bool host_out = io.host_out != 0;  // zero-copy outputs: the transposing epilogue runs instead of the plain one (see T4's note)
+    if (worker && !host_out) {
         const double* LAMp = c.LAM;
         constexpr int UB = 8;  // batched so that the loads of one batch are in flight together
         if (valid) {
@@ -1382,12 +1377,16 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
             }
         }
     }
-    if (valid && tid < I && io.stats) {
+    // statistics: to the caller's array, or -- zero-copy outputs -- to shared memory behind the transpose buffer for the epilogue
+    if (tid < I && io.stats && (valid || host_out)) {
         mmpc_stats s;
         s.objective = fval; s.kkt_error = err; s.mu = mu; s.iterations = it_done; s.status = status;
         s.ls_steps = ls_total; s.reg_steps = reg_total;
-        io.stats[b] = s;
+        mmpc_stats* dst = host_out ? reinterpret_cast<mmpc_stats*>(smem + I * 65) + tid : io.stats + b;
+        *dst = s;
     }
+    if (host_out)
+        t3_outputs_to_host_s(smem, io.V_out, io.lam_out, io.stats, io.b1, tile, I, NV, Mc, Vp - i, c.LAM - i, back ? Lcan - i : nullptr);
 #ifdef MMPC_T3_PROFILE_CTAS
     __syncthreads();
     if (threadIdx.x == 0) {

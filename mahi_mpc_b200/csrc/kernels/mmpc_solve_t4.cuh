@@ -415,8 +415,14 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
     c.V = W.V2 + (size_t)tile * I * NV + i; c.LAM = W.LAM2 + (size_t)tile * I * Mc + i;
     c.DV = W.DV2 + (size_t)tile * I * NV + i; c.LAMN = W.LAMN2 + (size_t)tile * I * Mc + i;
     c.LINp = W.LIN2 + (size_t)b * C::LIN;
-    const T3Inputs in = t3_stage_inputs<C::THREADS, NX, NU>(io, tid, max(tile * I, io.b0), min(tile * I + I, io.b1), N);
-    c.traj = in.traj + (size_t)bi * N * NX;
+    const double *in_state = io.state, *in_control = io.control;
+    c.traj = io.traj + (size_t)bi * N * NX;
+    if (io.traj_stage) {  // zero-copy inputs (uniform over the grid): the tile's rows are brought on the device first
+        t3_stage_inputs(io.state, io.control, io.traj, io.state_stage, io.control_stage, io.traj_stage, max(tile * I, io.b0),
+                        min(tile * I + I, io.b1), NX, NU, N);
+        in_state = io.state_stage; in_control = io.control_stage;
+        c.traj = io.traj_stage + (size_t)bi * N * NX;
+    }
     // node records of the tile: FG2, KG2, PG2 are one contiguous region of the arena (mmpc_api.cu), used here as [node][REC rows][I]
     double* fg_tile = W.FG2 + (size_t)tile * I * N * C::REC;
     double* kg_tile = fg_tile + (size_t)C::REC_K * I;
@@ -425,7 +431,7 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
     MMPC_UNROLL for (int a = 0; a < NU; ++a) {
         c.R[a] = W.Rw[(size_t)a * W.Bp + bi];
         c.Rm[a] = W.Rmw[(size_t)a * W.Bp + bi];
-        c.uinit[a] = in.control[(size_t)bi * NU + a];
+        c.uinit[a] = in_control[(size_t)bi * NU + a];
     }
     // ---- start point (ModelControl.cpp:28-50,68 cold; :161 warm), x_0 pinned (:144-145); the C workers of an instance help ----
     const bool warm = io.warm_start && W.have_warm;
@@ -433,7 +439,7 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
         if (!warm) for (int e = NX + j; e < NV; e += C::CB) c.V[(size_t)e * I] = 0.0;
         if (!(warm && io.warm_start_duals)) for (int e = j; e < Mc; e += C::CB) c.LAM[(size_t)e * I] = 0.0;
         for (int e = j; e < NX; e += C::CB) {
-            c.V[(size_t)e * I] = in.state[(size_t)bi * NX + e];
+            c.V[(size_t)e * I] = in_state[(size_t)bi * NX + e];
             c.DV[(size_t)e * I] = 0.0;
         }
     }
@@ -572,14 +578,12 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
     // steps the multipliers are copied back there ----
     double* const Lcan = W.LAM2 + (size_t)tile * I * Mc + i;
     const bool back = c.LAM != Lcan;  // tile-uniform
-    if (io.host_out) {
-        mmpc_stats s;
-        s.objective = fval; s.kkt_error = err; s.mu = 0.0; s.iterations = it_done; s.status = status;
-        s.ls_steps = ls_total; s.reg_steps = reg_total;
-        t3_outputs_to_host<C::THREADS, I>(smem, io, tile, tid, NV, Mc, Vp - i, c.LAM - i, back ? Lcan - i : nullptr, s);
-        return;
-    }
-    if (worker) {
+    // Zero-copy outputs (io.host_out, grid-uniform): the transposing epilogue t3_outputs_to_host_s runs instead of the plain one.  It is
+    // called at the very end, without an early return and without solver state among its arguments (the statistics go through
+    // shared memory): measured on one box at B = 4096, this form leaves the device-resident solve where it was (0.307 ms), an early
+    // `if (host_out) { ...; return; }` in front of the plain epilogue cost it 2.5 % (0.315 ms) -- profiles/r2_latency.txt.
+    const bool host_out = io.host_out != 0;
+    if (worker && !host_out) {
         const double* LAMp = c.LAM;
         constexpr int UB = 8;  // batched so that the loads of one batch are in flight together
         if (valid) {
@@ -599,12 +603,16 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
             }
         }
     }
-    if (valid && tid < I && io.stats) {
+    // statistics: to the caller's array, or -- zero-copy outputs -- to shared memory behind the transpose buffer for the epilogue
+    if (tid < I && io.stats && (valid || host_out)) {
         mmpc_stats s;
         s.objective = fval; s.kkt_error = err; s.mu = 0.0; s.iterations = it_done; s.status = status;
         s.ls_steps = ls_total; s.reg_steps = reg_total;
-        io.stats[b] = s;
+        mmpc_stats* dst = host_out ? reinterpret_cast<mmpc_stats*>(smem + I * 65) + tid : io.stats + b;
+        *dst = s;
     }
+    if (host_out)
+        t3_outputs_to_host_s(smem, io.V_out, io.lam_out, io.stats, io.b1, tile, I, NV, Mc, Vp - i, c.LAM - i, back ? Lcan - i : nullptr);
 #ifdef MMPC_T4_PROFILE
     __syncthreads();
 #ifdef MMPC_T4_PROFILE_CTAS

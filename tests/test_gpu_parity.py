@@ -722,7 +722,7 @@ def test_pinned_host_buffers_zero_copy_matches_device_resident(api):
         if bounded:
             s.set_bounds(u_min=[-2.0, -2.0], u_max=[2.0, 2.0])
         d = [torch.from_numpy(a).cuda() for a in (x0, up, traj)]
-        Vd, lamd, std = s.solve(*d)
+        Vd, lamd, std = s.solve(*d)  # stream-ordered on torch's current stream; the host-buffer call below waits for it (ev[3])
         h = [torch.from_numpy(a).pin_memory() for a in (x0, up, traj)]
         Vh = torch.empty(B, m.NV, dtype=torch.float64).pin_memory(); lamh = torch.empty(B, m.M, dtype=torch.float64).pin_memory()
         sth = torch.empty(B, 5, dtype=torch.float64).pin_memory()

@@ -17,7 +17,7 @@ def one(setting):
     import mahi_mpc_b200.api as api
     from mahi_mpc_b200 import workload as w
     out = {}
-    for (B, N) in ((1, 25), (1, 50), (4, 25), (32, 25), (32, 50), (64, 25)):
+    for (B, N) in (((1, 25), (1, 50), (4, 25), (32, 25), (32, 50), (64, 25)) if not os.environ.get('MMPC_LAT_SIZES') else [tuple(int(v) for v in t.split('x')) for t in os.environ['MMPC_LAT_SIZES'].split(',')]):
         x0, up, traj = w.synthetic_batch(4, 2, N, 0.002, B)
         Q, R, Rm = w.default_weights(4, 2)
         m = api.Model("double_pendulum", N=N)
