@@ -200,7 +200,8 @@ static __device__ __noinline__ void t3_stage_inputs(const double* state, const d
         t3_stage_rows(state + (size_t)bA * nx, state_stage + (size_t)bA * nx, ns, tid, nthreads);
         t3_stage_rows(control + (size_t)bA * nu, control_stage + (size_t)bA * nu, nc, tid, nthreads);
     }
-    t3_stage_rows(traj + (size_t)bA * N * nx, traj_stage + (size_t)bA * N * nx, nb * N * nx, tid, nthreads);
+    if (traj != traj_stage)  // (the trajectories may have been brought on the device by a copy engine already: MMPC_ZC_BIG=3)
+        t3_stage_rows(traj + (size_t)bA * N * nx, traj_stage + (size_t)bA * N * nx, nb * N * nx, tid, nthreads);
     if (small) {
         if (tid < ns) state_stage[(size_t)bA * nx + tid] = ts;
         if (tid < nc) control_stage[(size_t)bA * nu + tid] = tc;

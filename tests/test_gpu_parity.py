@@ -716,7 +716,7 @@ def test_pinned_host_buffers_zero_copy_matches_device_resident(api):
     import torch
     N = 50
     m = api.Model("double_pendulum", N=N)
-    for B, bounded in ((4096, False), (4096 + 37, False), (1500, False), (4096, True)):
+    for B, bounded in ((4096, False), (4096 + 37, False), (1500, False), (4096, True), (8192 + 5, False)):  # the last: two waves, copy engines, 8 pieces
         P, (Q, R, Rm), x0, up, traj, p = _solve_inputs(N, B)
         s = api.Solver(m, B, tol=1e-8, warm_start=0); s.set_weights(Q, R, Rm)
         if bounded:

@@ -46,8 +46,8 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "sweep":
         B = sys.argv[2] if len(sys.argv) > 2 else "4096"
         res = {}
-        for zc in ("0", "1", "2"):
-            for pipe in ("1", "2", "4", "8"):
+        for zc in os.environ.get("MMPC_SWEEP_ZC", "0,1,2,3").split(","):
+            for pipe in os.environ.get("MMPC_SWEEP_PIPE", "1,2,4,8").split(","):
                 env = dict(os.environ, MMPC_ZC_BIG=zc, MMPC_PIPE=pipe)
                 r = subprocess.run([sys.executable, "-m", "tools.e2e_time", B], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
                 line = [l for l in r.stdout.splitlines() if l.startswith("E2E ")]
