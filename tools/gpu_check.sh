@@ -1,10 +1,8 @@
 mkdir -p gpurun_out
-MMPC_SWEEP_ZC=0,2,3 MMPC_SWEEP_PIPE=4,8 timeout 600 python -m tools.e2e_time sweep 4096 2>&1 | grep "^zc="
-for m in 2 3; do
-MMPC_ZC_BIG=$m timeout 600 python bench.py --headline-only --no-cpu --steps 30 > gpurun_out/check_bench_$m.json 2> gpurun_out/check_bench.err; echo "bench mode $m rc $?"
-python - <<PY
+timeout 600 python bench.py > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/final_bench.err; echo "bench rc $?"
+python - <<'PY'
 import json
-d = json.loads(open("gpurun_out/check_bench_$m.json").read().strip().splitlines()[-1])
-print("mode $m value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"])
+d = json.loads(open("gpurun_out/r2_bench_1gpu.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], d["clocks"], d["latency"]["p50_us"], d["latency"]["cpu_port_p50_us"], d["latency"]["N50"]["p50_us"], d["latency"]["N50"]["cpu_port_p50_us"], d["cpu_baseline"]["value"], d["cpu_baseline"]["sample"][:60])
 PY
-done
+timeout 600 python -m pytest tests -m gpu -q -k "pinned_host or small_batch_packed" 2>&1 | tail -2
