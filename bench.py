@@ -305,6 +305,8 @@ def run_gpu(args):
         gathered = shard.gather_to_root([d_V, d_st])
         g1.record()
         barrier()
+        if rank == 0:  # rank r's block is rows [r B, (r + 1) B)
+            assert gathered[0].shape[0] == world * B and gathered[1].shape[0] == world * B and torch.equal(gathered[0][:B], d_V)
         t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gather_ms = t.item()
