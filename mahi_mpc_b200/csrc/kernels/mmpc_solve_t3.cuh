@@ -1357,7 +1357,12 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
     // steps the multipliers are copied back there ----
     double* const Lcan = W.LAM2 + (size_t)tile * I * Mc + i;
     const bool back = c.LAM != Lcan;  // tile-uniform
-    const bool host_out = io.host_out != 0;  // zero-copy outputs: the transposing epilogue runs instead of the plain one (see T4's note)
+#ifdef MMPC_WIDE_TILES_NO_HOSTOUT
+    constexpr bool HOST_OUT = I <= 8;  // wide tiles: the ABI layer fetches the outputs with a copy kernel behind this one
+#else
+    constexpr bool HOST_OUT = true;
+#endif
+    const bool host_out = HOST_OUT && io.host_out != 0;  // zero-copy outputs: the transposing epilogue runs instead of the plain one (see T4's note)
     if (worker && !host_out) {
         const double* LAMp = c.LAM;
         constexpr int UB = 8;  // batched so that the loads of one batch are in flight together
@@ -1386,7 +1391,7 @@ __global__ void __launch_bounds__(T3<M, I_, CB_, CF_, SK_, RK_>::THREADS) solve_
         mmpc_stats* dst = host_out ? reinterpret_cast<mmpc_stats*>(smem + I * 65) + tid : io.stats + b;
         *dst = s;
     }
-    if (host_out)
+    if constexpr (HOST_OUT) if (host_out)
         t3_outputs_to_host_s(smem, io.V_out, io.lam_out, io.stats, io.b1, tile, I, NV, Mc, Vp - i, c.LAM - i, back ? Lcan - i : nullptr);
 #ifdef MMPC_T3_PROFILE_CTAS
     __syncthreads();

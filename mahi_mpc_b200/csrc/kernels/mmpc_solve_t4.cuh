@@ -582,7 +582,12 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
     // called at the very end, without an early return and without solver state among its arguments (the statistics go through
     // shared memory): measured on one box at B = 4096, this form leaves the device-resident solve where it was (0.307 ms), an early
     // `if (host_out) { ...; return; }` in front of the plain epilogue cost it 2.5 % (0.315 ms) -- profiles/r2_latency.txt.
-    const bool host_out = io.host_out != 0;
+#ifdef MMPC_WIDE_TILES_NO_HOSTOUT
+    constexpr bool HOST_OUT = I <= 8;  // wide tiles: the ABI layer fetches the outputs with a copy kernel behind this one
+#else
+    constexpr bool HOST_OUT = true;
+#endif
+    const bool host_out = HOST_OUT && io.host_out != 0;
     if (worker && !host_out) {
         const double* LAMp = c.LAM;
         constexpr int UB = 8;  // batched so that the loads of one batch are in flight together
@@ -611,7 +616,7 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
         mmpc_stats* dst = host_out ? reinterpret_cast<mmpc_stats*>(smem + I * 65) + tid : io.stats + b;
         *dst = s;
     }
-    if (host_out)
+    if constexpr (HOST_OUT) if (host_out)
         t3_outputs_to_host_s(smem, io.V_out, io.lam_out, io.stats, io.b1, tile, I, NV, Mc, Vp - i, c.LAM - i, back ? Lcan - i : nullptr);
 #ifdef MMPC_T4_PROFILE
     __syncthreads();
