@@ -614,11 +614,13 @@ struct Launch {
     extern "C" cudaError_t mmpc_solve_t4p1_##MODEL(MMPC_SOLVE_FN_ARGS);                                                 \
     extern "C" cudaError_t mmpc_solve_t4p2_##MODEL(MMPC_SOLVE_FN_ARGS);                                                 \
     extern "C" cudaError_t mmpc_solve_t4p3_##MODEL(MMPC_SOLVE_FN_ARGS);                                                 \
+    extern "C" cudaError_t mmpc_solve_t4p4_##MODEL(MMPC_SOLVE_FN_ARGS);                                                 \
     extern "C" cudaError_t mmpc_solve_t4_##MODEL(MMPC_SOLVE_FN_ARGS) {                                                  \
         const int part = mmpc::LaunchT4<mmpc_model_##MODEL>::part_of(*P, *W, *io);                                      \
         if (part == 1) return MMPC_T4_EXTRA_PART(MODEL, 1);                                                             \
         if (part == 2) return mmpc_solve_t4p2_##MODEL(P, W, io, st);                                                    \
         if (part == 3) return MMPC_T4_EXTRA_PART(MODEL, 3);                                                             \
+        if (part == 4) return mmpc_solve_t4p4_##MODEL(P, W, io, st);                                                    \
         return mmpc::Launch<mmpc_model_##MODEL>::solve_t4<0>(*P, *W, *io, st);                                          \
     }
 #define MMPC_DEFINE_SOLVE_T4_PART(MODEL, K)                                                                            \
@@ -657,6 +659,7 @@ struct Launch {
     MMPC_DEFINE_SOLVE_T1(MODEL) MMPC_DEFINE_SOLVE_T1B(MODEL) MMPC_DEFINE_SOLVE_T2(MODEL)                                  \
     MMPC_DEFINE_SOLVE_T3(MODEL) MMPC_DEFINE_SOLVE_T3_PART(MODEL, 1) MMPC_DEFINE_SOLVE_T3_PART(MODEL, 2)                    \
     MMPC_DEFINE_SOLVE_T4(MODEL) MMPC_DEFINE_SOLVE_T4_PART(MODEL, 1) MMPC_DEFINE_SOLVE_T4_PART(MODEL, 2) MMPC_DEFINE_SOLVE_T4_PART(MODEL, 3) \
+    MMPC_DEFINE_SOLVE_T4_PART(MODEL, 4)                                                                                   \
     MMPC_DEFINE_MODEL_CORE(MODEL)
 // Additionally exports the generic entry point a stand-alone generated model library is dlopen'ed by
 // (the role `nlpsol("nlpsol","ipopt",dll,...)` plays at ModelControl.cpp:61-62).

@@ -382,7 +382,10 @@ __device__ __noinline__ bool t4_armijo(const T3Ctx<M, C::I, C::MODE>& c, double*
     return true;
 }
 
-template <class M, int I_, int CB_, int CF_, int RK_, int SK_>
+// HO_: the instantiation that can write its outputs to host memory in place (zero-copy epilogue).  The kernels sit at 255
+// registers, and the mere presence of the epilogue call costs the device-resident solve 2 % (profiles/r2_zero_copy_experiments.txt):
+// the default tile shapes are therefore instantiated twice, and the launcher picks by io.host_out.
+template <class M, int I_, int CB_, int CF_, int RK_, int SK_, bool HO_ = true>
 __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_kernel_t4(mmpc_problem P, mmpc_workspace W, mmpc_solve_io io) {
     using C = T4<M, I_, CB_, CF_, RK_, SK_>;
     constexpr int NX = M::NX, NU = M::NU, S = C::S, I = C::I;
@@ -583,9 +586,9 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
     // shared memory): measured on one box at B = 4096, this form leaves the device-resident solve where it was (0.307 ms), an early
     // `if (host_out) { ...; return; }` in front of the plain epilogue cost it 2.5 % (0.315 ms) -- profiles/r2_latency.txt.
 #ifdef MMPC_WIDE_TILES_NO_HOSTOUT
-    constexpr bool HOST_OUT = I <= 8;  // wide tiles: the ABI layer fetches the outputs with a copy kernel behind this one
+    constexpr bool HOST_OUT = HO_ && I <= 8;  // experiment: the ABI layer fetches wide tiles' outputs with a copy kernel (MMPC_ZC_OUT_KERNEL)
 #else
-    constexpr bool HOST_OUT = true;
+    constexpr bool HOST_OUT = HO_;
 #endif
     const bool host_out = HOST_OUT && io.host_out != 0;
     if (worker && !host_out) {
@@ -636,21 +639,22 @@ __global__ void __launch_bounds__(T4<M, I_, CB_, CF_, RK_, SK_>::THREADS) solve_
 
 template <class M>
 struct LaunchT4 {
-    template <int I_, int CB_, int CF_, int RK_ = 0, int SK_ = 0>
+    template <int I_, int CB_, int CF_, int RK_ = 0, int SK_ = 0, bool HO_ = true>
     static cudaError_t go(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         using C = T4<M, I_, CB_, CF_, RK_, SK_>;
         static_assert(C::SMEM_BYTES <= 227 * 1024, "record buffers must fit the 227 KB of shared memory a CTA can opt into");
+        if (io.host_out && !HO_) return cudaErrorInvalidValue;  // the launcher's part selection pairs host_out with an HO_ instantiation
         static std::atomic<unsigned long long> attr_done{0};
         int dev = 0;
         cudaGetDevice(&dev);
         if (C::SMEM_BYTES > 48 * 1024 && !((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ULL)) {
-            cudaError_t e = cudaFuncSetAttribute(solve_kernel_t4<M, I_, CB_, CF_, RK_, SK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+            cudaError_t e = cudaFuncSetAttribute(solve_kernel_t4<M, I_, CB_, CF_, RK_, SK_, HO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
             if (e != cudaSuccess) return e;
             attr_done.fetch_or(1ULL << (dev & 63), std::memory_order_release);
         }
         if (io.b0 % C::I != 0) return cudaErrorInvalidValue;  // sub-batches must start on a tile boundary
         const int t0 = io.b0 / C::I, t1 = (io.b1 + C::I - 1) / C::I;
-        solve_kernel_t4<M, I_, CB_, CF_, RK_, SK_><<<t1 - t0, C::THREADS, C::SMEM_BYTES, st>>>(P, W, io);
+        solve_kernel_t4<M, I_, CB_, CF_, RK_, SK_, HO_><<<t1 - t0, C::THREADS, C::SMEM_BYTES, st>>>(P, W, io);
         return cudaGetLastError();
     }
     // Tile width from the batch of the handle (mmpc_t4_tile_width; it fixes the layout of the persistent iterate):
@@ -666,16 +670,19 @@ struct LaunchT4 {
     // ModelGenerator::compile_model and the library build compile the units side by side):
     //   part 0  Euler / linearised, tile widths 4 and 32 (the defaults)     part 1  Euler / linearised, widths 8 and 28
     //   part 2  RK4 shooting, widths 4 and 32                               part 3  RK4 shooting, widths 8 and 28
+    //   part 4  = part 0 with the zero-copy output epilogue (io.host_out); part 0 itself is instantiated without it
     static int part_of(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io) {
         const int I = mmpc_t4_tile_width(W.B, io.variant >> 8);
-        return ((P.integrator == MMPC_RK4 && !P.is_linear) ? 2 : 0) + ((I == 4 || I == 32) ? 0 : 1);
+        const int part = ((P.integrator == MMPC_RK4 && !P.is_linear) ? 2 : 0) + ((I == 4 || I == 32) ? 0 : 1);
+        return part == 0 && io.host_out ? 4 : part;
     }
     template <int PART>
     static cudaError_t run_part(const mmpc_problem& P, const mmpc_workspace& W, const mmpc_solve_io& io, cudaStream_t st) {
         if (P.bounded) return cudaErrorNotSupported;
         if constexpr (M::NX + 2 * M::NU <= 8) {
             const int I = mmpc_t4_tile_width(W.B, io.variant >> 8);
-            if constexpr (PART == 0) return I == 4 ? go<4, 8, 8>(P, W, io, st) : go<32, 7, 5>(P, W, io, st);
+            if constexpr (PART == 0) return I == 4 ? go<4, 8, 8, 0, 0, false>(P, W, io, st) : go<32, 7, 5, 0, 0, false>(P, W, io, st);
+            if constexpr (PART == 4) return I == 4 ? go<4, 8, 8>(P, W, io, st) : go<32, 7, 5>(P, W, io, st);
             if constexpr (PART == 1) return I == 8 ? go<8, 4, 4>(P, W, io, st) : go<28, 8, 6>(P, W, io, st);
             if constexpr (PART == 2) return I == 4 ? go<4, 8, 5, 1>(P, W, io, st) : go<32, 7, 5, 1>(P, W, io, st);
             if constexpr (PART == 3) return I == 8 ? go<8, 4, 4, 1>(P, W, io, st) : go<28, 8, 5, 1>(P, W, io, st);
