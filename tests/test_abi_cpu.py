@@ -35,6 +35,12 @@ def test_header_symbols_all_exported(api):
     assert not missing, missing
     assert sorted(api.ABI_SYMBOLS) == declared
     assert lib.mmpc_abi_version() == 1
+    # ... and nothing else of the library's own: the per-model launchers / vtable getters of the kernel units are internal
+    import shutil, subprocess
+    if shutil.which("nm"):
+        out = subprocess.run(["nm", "-D", "--defined-only", api.LIB_PATH], capture_output=True, text=True).stdout
+        exported = sorted({ln.split()[-1] for ln in out.splitlines() if " T " in ln and ln.split()[-1].startswith("mmpc_")})
+        assert exported == declared, sorted(set(exported) ^ set(declared))
 
 
 def test_options_default_are_the_reference_ipopt_options(api):
